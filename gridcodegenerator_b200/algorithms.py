@@ -1,0 +1,430 @@
+"""The five rigid-body-dynamics algorithms, traced symbolically per robot.
+
+Each ``trace_*`` function builds a :class:`~gridcodegenerator_b200.ir.Program` whose
+inputs are the per-state scalars (``q_i``, ``qd_i``, ``u_i``/``qdd_i``, ``gravity``) and
+whose outputs are laid out exactly as the reference kernels write them
+(SURVEY.md 8a a9): ``c[n]``, ``Minv[n*n]`` column-major upper-triangular, ``qdd[n]``,
+``dc_du[2n*n]`` / ``df_du[2n*n]`` column-major ``n x 2n``.
+
+What each function replaces in the reference:
+  SymRobot              helpers/_topology_helpers.py:90-182 (per-q X update) and the
+                        mx*/fx* device helpers of helpers/_spatial_algebra_helpers.py:35-256
+  rnea / trace_id       algorithms/_inverse_dynamics.py:33-304  (oracle _test.py:5-115)
+  minv / trace_minv     algorithms/_direct_minv.py:23-382       (oracle _test.py:117-226)
+  trace_fd              algorithms/_forward_dynamics.py:21-112
+  rnea_grad_columns     algorithms/_inverse_dynamics_gradient.py:27-650 (oracle _test.py:229-488)
+  trace_fd_grad         algorithms/_forward_dynamics_gradient.py:7-57   (oracle _test.py:496-520)
+
+Structure exploited at trace time (the reference multiplies dense 6x6 matrices):
+X = [[E,0],[-E r^x,E]] is applied as a constant 3x3 (X_tree, usually a signed
+permutation) followed by a planar rotation; spatial inertias and articulated
+inertias are kept symmetric; topology (parents, subtrees, ancestor sets) is resolved
+in Python so no index arithmetic reaches the GPU.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .ir import Program, V, cross3, dot, matvec, vadd, vsub, vscale, zeros
+from .robot import Robot
+
+
+class SymRobot:
+    """Per-state symbolic view of the robot: sin/cos of q and the X_i(q) actions."""
+
+    def __init__(self, p: Program, robot: Robot, q: Sequence[V]):
+        self.p, self.robot, self.n = p, robot, robot.n
+        self.q = list(q)
+        self.sin: List[Optional[V]] = []
+        self.cos: List[Optional[V]] = []
+        self.r: List[List[V]] = []
+        for i in range(self.n):
+            k = robot.S_ind[i]
+            E0, r0 = robot.E0[i], robot.r0[i]
+            if k < 3:
+                self.sin.append(p.sin(q[i]))
+                self.cos.append(p.cos(q[i]))
+                self.r.append([p.const(x) for x in r0])
+            else:   # prismatic: r = r0 + q * E0[k-3, :]
+                self.sin.append(None)
+                self.cos.append(None)
+                self.r.append([p.const(r0[t]) + q[i] * float(E0[k - 3, t]) for t in range(3)])
+        self.I = [[[p.const(x) for x in row] for row in robot.Imats[i]] for i in range(self.n)]
+
+    # -- rotations ---------------------------------------------------------------
+    def _EJ(self, i: int, y: Sequence[V], transpose: bool) -> List[V]:
+        k = self.robot.S_ind[i]
+        if k >= 3:
+            return list(y)
+        a, b = (k + 1) % 3, (k + 2) % 3
+        c, s = self.cos[i], self.sin[i]
+        if transpose:
+            s = -s
+        out = list(y)
+        out[a] = c * y[a] + s * y[b]
+        out[b] = c * y[b] - s * y[a]
+        return out
+
+    def E(self, i: int, x: Sequence[V]) -> List[V]:
+        E0 = self.robot.E0[i]
+        y = [dot([self.p.const(E0[r, t]) for t in range(3)], x) for r in range(3)]
+        return self._EJ(i, y, False)
+
+    def ET(self, i: int, y: Sequence[V]) -> List[V]:
+        E0 = self.robot.E0[i]
+        z = self._EJ(i, y, True)
+        return [dot([self.p.const(E0[t, r]) for t in range(3)], z) for r in range(3)]
+
+    # -- spatial transforms --------------------------------------------------------
+    def X_motion(self, i: int, v: Sequence[V]) -> List[V]:
+        """X_i v for a motion vector (also how the reference moves F columns forward)."""
+        w, l = v[:3], v[3:]
+        return self.E(i, w) + self.E(i, vsub(l, cross3(self.r[i], w)))
+
+    def XT_force(self, i: int, f: Sequence[V]) -> List[V]:
+        """X_i^T f for a force vector."""
+        fl = self.ET(i, f[3:])
+        return vadd(self.ET(i, f[:3]), cross3(self.r[i], fl)) + fl
+
+    def X_col(self, i: int, col: int, scale) -> List[V]:
+        """scale * X_i[:, col]  (root acceleration: X[:,5]*gravity)."""
+        e = zeros(self.p, 6)
+        e[col] = self.p.lift(scale)
+        return self.X_motion(i, e)
+
+    def I_mul(self, i: int, v: Sequence[V]) -> List[V]:
+        return matvec(self.I[i], v)
+
+    def congruence(self, i: int, M: List[List[V]]) -> List[List[V]]:
+        """X_i^T M X_i for a symmetric 6x6 M, returned symmetric (upper triangle
+        computed, mirrored)."""
+        p = self.p
+        A = [[M[r][c] for c in range(3)] for r in range(3)]
+        B = [[M[r][c + 3] for c in range(3)] for r in range(3)]
+        C = [[M[r + 3][c + 3] for c in range(3)] for r in range(3)]
+
+        def rot(Mb, symmetric):
+            cols = [self.ET(i, [Mb[r][c] for r in range(3)]) for c in range(3)]   # E^T Mb, by column
+            T1 = [[cols[c][r] for c in range(3)] for r in range(3)]
+            rows = [self.ET(i, T1[r]) for r in range(3)]                           # (E^T Mb) E, by row
+            if symmetric:
+                for r in range(3):
+                    for c in range(r):
+                        rows[r][c] = rows[c][r]
+            return rows
+
+        A1, B1, C1 = rot(A, True), rot(B, False), rot(C, True)
+        r = self.r[i]
+        rx = [[p.const(0.0), -r[2], r[1]], [r[2], p.const(0.0), -r[0]], [-r[1], r[0], p.const(0.0)]]
+
+        def mm(P, Q):
+            return [[dot(P[a], [Q[t][b] for t in range(3)]) for b in range(3)] for a in range(3)]
+
+        rxC = mm(rx, C1)
+        B2 = [[B1[a][b] + rxC[a][b] for b in range(3)] for a in range(3)]
+        B1rx = mm(B1, rx)
+        rxB2T = mm(rx, [[B2[b][a] for b in range(3)] for a in range(3)])
+        A2 = [[None] * 3 for _ in range(3)]
+        for a in range(3):
+            for b in range(a, 3):
+                A2[a][b] = A1[a][b] - B1rx[a][b] + rxB2T[a][b]
+                A2[b][a] = A2[a][b]
+        out = [[None] * 6 for _ in range(6)]
+        for a in range(3):
+            for b in range(3):
+                out[a][b] = A2[a][b]
+                out[a][b + 3] = B2[a][b]
+                out[b + 3][a] = B2[a][b]
+                out[a + 3][b + 3] = C1[a][b]
+        return out
+
+
+def cross_motion_axis(p: Program, k: int, v: Sequence[V], alpha=None) -> List[V]:
+    """(v x) e_k [* alpha]  - the reference's mx0..mx5 (helpers/_spatial_algebra_helpers.py:62-147)."""
+    e = [p.const(1.0 if t == (k % 3) else 0.0) for t in range(3)]
+    if k < 3:
+        out = cross3(v[:3], e) + cross3(v[3:], e)
+    else:
+        out = zeros(p, 3) + cross3(v[:3], e)
+    return out if alpha is None else vscale(out, alpha)
+
+
+def cross_force(v: Sequence[V], f: Sequence[V]) -> List[V]:
+    """v x* f  - fx_times_v (helpers/_spatial_algebra_helpers.py:181-256)."""
+    return vadd(cross3(v[:3], f[:3]), cross3(v[3:], f[3:])) + cross3(v[:3], f[3:])
+
+
+# ---- RNEA -------------------------------------------------------------------------
+class RneaResult:
+    __slots__ = ("c", "v", "a", "f", "Xa", "Iv")
+
+
+def rnea(sr: SymRobot, qd: Sequence[V], qdd: Optional[Sequence[V]], gravity: V) -> RneaResult:
+    p, robot, n = sr.p, sr.robot, sr.n
+    v: List[List[V]] = [None] * n
+    a: List[List[V]] = [None] * n
+    Xa: List[List[V]] = [None] * n
+    f: List[List[V]] = [None] * n
+    Iv: List[List[V]] = [None] * n
+    for i in range(n):
+        par, k = robot.parent[i], robot.S_ind[i]
+        if par < 0:
+            v[i] = zeros(p, 6)
+            Xa[i] = sr.X_col(i, 5, gravity)
+        else:
+            v[i] = sr.X_motion(i, v[par])
+            Xa[i] = sr.X_motion(i, a[par])
+        v[i][k] = v[i][k] + qd[i]
+        a[i] = list(Xa[i])
+        if qdd is not None:
+            a[i][k] = a[i][k] + qdd[i]
+        if par >= 0:
+            a[i] = vadd(a[i], cross_motion_axis(p, k, v[i], qd[i]))
+        Iv[i] = sr.I_mul(i, v[i])
+        f[i] = vadd(sr.I_mul(i, a[i]), cross_force(v[i], Iv[i]))
+    c = [None] * n
+    for i in range(n - 1, -1, -1):
+        c[i] = f[i][robot.S_ind[i]] + qd[i] * robot.damping[i]
+        par = robot.parent[i]
+        if par >= 0:
+            f[par] = vadd(f[par], sr.XT_force(i, f[i]))
+    res = RneaResult()
+    res.c, res.v, res.a, res.f, res.Xa, res.Iv = c, v, a, f, Xa, Iv
+    return res
+
+
+# ---- Minv ---------------------------------------------------------------------------
+def minv(sr: SymRobot) -> Dict[Tuple[int, int], V]:
+    """Upper-triangular M^-1 as {(row, col): V}, col >= row."""
+    p, robot, n = sr.p, sr.robot, sr.n
+    zero6 = lambda: zeros(p, 6)
+    Mi: Dict[Tuple[int, int], V] = {}
+    F: List[Dict[int, List[V]]] = [dict() for _ in range(n)]       # F[i][col] -> 6-vector
+    U: List[List[V]] = [None] * n
+    Dinv: List[V] = [None] * n
+    IA = [[list(row) for row in sr.I[i]] for i in range(n)]
+    for i in range(n - 1, -1, -1):
+        k, par = robot.S_ind[i], robot.parent[i]
+        sub = robot.get_subtree_by_id(i)
+        U[i] = [IA[i][r][k] for r in range(6)]
+        Dinv[i] = p.rcp(U[i][k])
+        for j in sub:
+            Fij = F[i].get(j)
+            Mi[(i, j)] = (Dinv[i] if j == i else p.const(0.0)) - (Dinv[i] * Fij[k] if Fij is not None else 0.0)
+        if par >= 0:
+            for j in sub:
+                Fij = vadd(F[i].get(j, zero6()), vscale(U[i], Mi[(i, j)]))
+                F[i][j] = Fij
+                F[par][j] = vadd(F[par].get(j, zero6()), sr.XT_force(i, Fij))
+            UD = vscale(U[i], Dinv[i])
+            Ia = [[None] * 6 for _ in range(6)]
+            for r in range(6):
+                for c in range(r, 6):
+                    Ia[r][c] = IA[i][r][c] - UD[r] * U[i][c]
+                    Ia[c][r] = Ia[r][c]
+            Ip = sr.congruence(i, Ia)
+            IA[par] = [[IA[par][r][c] + Ip[r][c] for c in range(6)] for r in range(6)]
+    for i in range(n):
+        k, par = robot.S_ind[i], robot.parent[i]
+        cols = range(i, n)
+        if par >= 0:
+            w = vscale(sr.XT_force(i, U[i]), Dinv[i])                 # Dinv * X^T U
+            for j in cols:
+                Fpj = F[par].get(j)
+                if Fpj is not None:
+                    Mi[(i, j)] = Mi.get((i, j), p.const(0.0)) - dot(w, Fpj)
+        for j in cols:
+            m = Mi.get((i, j), p.const(0.0))
+            Mi[(i, j)] = m
+            Fij = zero6()
+            Fij[k] = m
+            if par >= 0 and F[par].get(j) is not None:
+                Fij = vadd(Fij, sr.X_motion(i, F[par][j]))
+            F[i][j] = Fij
+    return Mi
+
+
+def minv_get(Mi: Dict[Tuple[int, int], V], r: int, c: int) -> V:
+    return Mi[(r, c)] if r <= c else Mi[(c, r)]
+
+
+# ---- RNEA gradient -------------------------------------------------------------------
+def rnea_grad_columns(sr: SymRobot, qd: Sequence[V], R: RneaResult):
+    """Yields (j, dc_dq_col, dc_dqd_col) one du-column pair at a time; each col is a
+    dict {row i: V} over anc(j) | sub(j) (structural zeros elsewhere).  Columns are
+    independent through both passes, which is what lets the emitter finish and store
+    one column before starting the next."""
+    p, robot, n = sr.p, sr.robot, sr.n
+    for j in range(n):
+        kj = robot.S_ind[j]
+        sub = robot.get_subtree_by_id(j)
+        dv = {0: {}, 1: {}}
+        da = {0: {}, 1: {}}
+        df = {0: {}, 1: {}}
+        for i in sub:
+            k = robot.S_ind[i]
+            if i == j:
+                dv[0][i] = cross_motion_axis(p, k, R.v[i])              # == mxS(X v_parent)
+                e = zeros(p, 6)
+                e[k] = p.const(1.0)
+                dv[1][i] = e
+                da[0][i] = vadd(cross_motion_axis(p, k, dv[0][i], qd[i]), cross_motion_axis(p, k, R.Xa[i]))
+                da[1][i] = cross_motion_axis(p, k, R.v[i])
+            else:
+                par = robot.parent[i]
+                for s in (0, 1):
+                    dv[s][i] = sr.X_motion(i, dv[s][par])
+                    da[s][i] = vadd(sr.X_motion(i, da[s][par]), cross_motion_axis(p, k, dv[s][i], qd[i]))
+            for s in (0, 1):
+                df[s][i] = vadd(vadd(sr.I_mul(i, da[s][i]), cross_force(dv[s][i], R.Iv[i])),
+                                cross_force(R.v[i], sr.I_mul(i, dv[s][i])))
+        cols = ({}, {})
+        for i in reversed(sub):
+            par = robot.parent[i]
+            for s in (0, 1):
+                cols[s][i] = df[s][i][robot.S_ind[i]]
+            if i != j:
+                for s in (0, 1):
+                    df[s][par] = vadd(df[s][par], sr.XT_force(i, df[s][i]))
+        # leave the subtree: the dq column also carries -X_j^T (f_j x) S_j
+        up = [vsub(df[0][j], cross_motion_axis(p, kj, R.f[j])), df[1][j]]
+        i = j
+        while robot.parent[i] >= 0:
+            up = [sr.XT_force(i, up[0]), sr.XT_force(i, up[1])]
+            i = robot.parent[i]
+            for s in (0, 1):
+                cols[s][i] = up[s][robot.S_ind[i]]
+        cols[1][j] = cols[1][j] + robot.damping[j]
+        yield j, cols[0], cols[1]
+
+
+# ---- traced programs -------------------------------------------------------------------
+def _inputs(p: Program, n: int, names: Sequence[str]):
+    return [[p.inp("%s%d" % (nm, i)) for i in range(n)] for nm in names]
+
+
+def trace_id(robot: Robot, use_qdd: bool = False) -> Program:
+    p = Program()
+    n = robot.n
+    q, qd = _inputs(p, n, ("q", "qd"))
+    qdd = _inputs(p, n, ("qdd",))[0] if use_qdd else None
+    g = p.inp("gravity")
+    R = rnea(SymRobot(p, robot, q), qd, qdd, g)
+    for i in range(n):
+        p.output("c", i, R.c[i])
+    return p
+
+
+def trace_minv(robot: Robot) -> Program:
+    p = Program()
+    n = robot.n
+    (q,) = _inputs(p, n, ("q",))
+    Mi = minv(SymRobot(p, robot, q))
+    for col in range(n):
+        for row in range(n):
+            p.output("Minv", col * n + row, Mi[(row, col)] if row <= col else 0.0)
+    return p
+
+
+def trace_fd(robot: Robot) -> Program:
+    p = Program()
+    n = robot.n
+    q, qd, u = _inputs(p, n, ("q", "qd", "u"))
+    g = p.inp("gravity")
+    sr = SymRobot(p, robot, q)
+    R = rnea(sr, qd, None, g)
+    Mi = minv(sr)
+    umc = [u[i] - R.c[i] for i in range(n)]
+    for i in range(n):
+        p.output("qdd", i, dot([minv_get(Mi, i, j) for j in range(n)], umc))
+    return p
+
+
+def trace_id_grad(robot: Robot, use_qdd: bool = False) -> Program:
+    p = Program()
+    n = robot.n
+    q, qd = _inputs(p, n, ("q", "qd"))
+    qdd = _inputs(p, n, ("qdd",))[0] if use_qdd else None
+    g = p.inp("gravity")
+    sr = SymRobot(p, robot, q)
+    R = rnea(sr, qd, qdd, g)
+    for j, cq, cqd in rnea_grad_columns(sr, qd, R):
+        for i in range(n):
+            p.output("dc_du", n * j + i, cq.get(i, 0.0))
+        for i in range(n):
+            p.output("dc_du", n * n + n * j + i, cqd.get(i, 0.0))
+    return p
+
+
+def trace_fd_grad(robot: Robot, use_qdd_minv: bool = False) -> Program:
+    """df_du = -Minv dc_du.  use_qdd_minv=False: inputs (q, qd, u), everything computed
+    in one program.  True: inputs (q, qd, qdd, Minv) - the USE_QDD_MINV_FLAG overload
+    (algorithms/_forward_dynamics_gradient.py:22-25, 202-220); Minv is read
+    symmetrically from its upper triangle (algorithms/_forward_dynamics.py:44)."""
+    p = Program()
+    n = robot.n
+    q, qd = _inputs(p, n, ("q", "qd"))
+    g = p.inp("gravity")
+    sr = SymRobot(p, robot, q)
+    if use_qdd_minv:
+        qdd = _inputs(p, n, ("qdd",))[0]
+        Mi = {(r, c): p.inp("Minv%d" % (c * n + r)) for r in range(n) for c in range(r, n)}
+    else:
+        (u,) = _inputs(p, n, ("u",))
+        R0 = rnea(sr, qd, None, g)
+        Mi = minv(sr)
+        umc = [u[i] - R0.c[i] for i in range(n)]
+        qdd = [dot([minv_get(Mi, i, j) for j in range(n)], umc) for i in range(n)]
+    R = rnea(sr, qd, qdd, g)
+    for j, cq, cqd in rnea_grad_columns(sr, qd, R):
+        for s, col in ((0, cq), (1, cqd)):
+            rows = sorted(col)
+            for i in range(n):
+                acc = dot([minv_get(Mi, i, r) for r in rows], [col[r] for r in rows])
+                p.output("df_du", s * n * n + n * j + i, -acc)
+    return p
+
+
+TRACERS = {
+    "id": lambda robot: trace_id(robot, False),
+    "id_qdd": lambda robot: trace_id(robot, True),
+    "minv": trace_minv,
+    "fd": trace_fd,
+    "id_grad": lambda robot: trace_id_grad(robot, False),
+    "id_grad_qdd": lambda robot: trace_id_grad(robot, True),
+    "fd_grad": lambda robot: trace_fd_grad(robot, False),
+    "fd_grad_qdd_minv": lambda robot: trace_fd_grad(robot, True),
+}
+
+
+# ---- algorithmic (dense-reference) work, SURVEY.md 8d -------------------------------------
+def algorithmic_flops(robot: Robot) -> Dict[str, int]:
+    """Dense 6x6 op count of the reference algorithm restricted to topological
+    non-zero columns (SURVEY.md 8d closed forms)."""
+    n = robot.n
+    anc = [len(robot.get_ancestors_by_id(i)) for i in range(n)]
+    sub = [len(robot.get_subtree_by_id(i)) for i in range(n)]
+    nonroot = [i for i in range(n) if robot.parent[i] >= 0]
+    L, n0 = len(nonroot), n - len(nonroot)
+    A = sum(anc)
+    D = A + n
+    B = sum(anc[i] + sub[i] for i in nonroot)
+    XI = 36 * n
+    ID = 168 * n + 224 * L + 7 * n0
+    MINV = n + 2 * sum(sub) + sum(936 + 78 * sub[i] for i in nonroot) + 80 * sum(n - i for i in nonroot)
+    IDG = 456 * n + 276 * A + 356 * D + 168 * B
+    return {
+        "id": XI + ID,
+        "minv": XI + MINV,
+        "fd": XI + MINV + ID + 3 * n * n,
+        "id_grad": XI + ID + IDG,
+        "fd_grad": XI + MINV + 2 * ID + 3 * n * n + IDG + 4 * n ** 3,
+    }
+
+
+def algorithmic_bytes(robot: Robot) -> Dict[str, int]:
+    n = robot.n
+    return {"id": 12 * n, "minv": 4 * (n + n * n), "fd": 16 * n, "id_grad": 4 * (2 * n + 2 * n * n),
+            "fd_grad": 4 * (3 * n + 2 * n * n)}
