@@ -1,0 +1,343 @@
+#!/usr/bin/env python3
+"""Benchmark: forward-dynamics-gradient evals/s, iiwa14, 65,536 states per GPU (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, one process per GPU)
+  python bench.py --impl reference [...]                         reference CPU path (numpy oracle port)
+
+One "step" = one pass of the hot path (one kernel launch) over one batch of synthetic states.
+Prints ONE JSON line on rank 0.  See DESIGN.md section "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROBOT = "iiwa14"
+ALG = "fd_grad"
+BATCH = 65536
+GRAVITY = 9.81
+METRIC = "fd_grad_evals_per_s_iiwa14_N65536"
+UNIT = "evals/s"
+FP32_THEORETICAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12       # 74.4, SURVEY.md 8d
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--robot", default=ROBOT)
+    ap.add_argument("--alg", default=ALG)
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="states in the CPU baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference path: the oracle port of the reference's numpy implementation (_test.py)
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    robot_name, alg, seed, count = args
+    from gridcodegenerator_b200 import load_named_robot
+    from gridcodegenerator_b200.synthetic import make_states
+    from oracle import rbd_numpy as O
+    robot = load_named_robot(robot_name)
+    q, qd, u, _ = (x.astype(np.float64) for x in make_states(robot.n, count, seed))
+    t0 = time.perf_counter()
+    O.batch(robot, alg, q, qd, u if alg in ("fd", "fd_grad") else None, GRAVITY)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_pass(robot_name, alg, total_states, cores, pool):
+    """One bounded sample of the workload over `cores` processes; returns (evals/s, single-core ms/eval)."""
+    per = max(1, total_states // cores)
+    jobs = [(robot_name, alg, 1000 + i, per) for i in range(cores)]
+    t0 = time.perf_counter()
+    times = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    return per * cores / wall, 1e3 * float(np.mean(times)) / per, per * cores
+
+
+def run_reference_arm(a):
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = a.cpu_sample or cores * 48
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(max(1, min(a.warmup, 1))):
+            cpu_reference_pass(a.robot, a.alg, cores * 4, cores, pool)
+        vals, t0 = [], time.perf_counter()
+        for _ in range(a.steps):
+            v, ms1, done = cpu_reference_pass(a.robot, a.alg, sample, cores, pool)
+            vals.append(v)
+        wall = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s %s, bounded sample of %d states per step (full batch %d)" % (
+            a.robot, a.alg, done, a.batch)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d seeded states per step over %d processes, oracle/rbd_numpy.py "
+                                   "(port of reference _test.py:496-520), single-core %.2f ms/eval" % (done, cores, ms1)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_lo, t_hi):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t_lo <= t <= t_hi] or [r for (_, r) in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_b200_arm(a):
+    import torch
+    import torch.distributed as dist
+    from gridcodegenerator_b200 import load_named_robot
+    from gridcodegenerator_b200.algorithms import algorithmic_bytes, algorithmic_flops
+    from gridcodegenerator_b200.runtime import get_engine
+    from gridcodegenerator_b200.synthetic import make_states, pack_q_qd_u, seed_for
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    robot = load_named_robot(a.robot)
+    eng = get_engine(robot)
+    n, N = robot.n, a.batch
+    in_words, out_words = 3 * n, {"id": n, "minv": n * n, "fd": n, "id_grad": 2 * n * n, "fd_grad": 2 * n * n}[a.alg]
+
+    # every rank owns its own contiguous slice of the global batch (weak scaling: BATCH states per GPU)
+    q, qd, u, _ = make_states(n, N, seed_for(a.robot) + 100 * rank)
+    host_in = pack_q_qd_u(q, qd, u)
+    # rotate over enough buffer sets that the working set exceeds the 126 MB L2
+    set_bytes = 4 * N * (in_words + out_words)
+    nsets = max(2, int(np.ceil(300e6 / set_bytes)))
+    ins = [torch.from_numpy(host_in).cuda() for _ in range(nsets)]
+    outs = [torch.empty(N, out_words, device="cuda") for _ in range(nsets)]
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        k = i % nsets
+        if a.alg == "fd_grad":
+            eng.forward_dynamics_gradient_device(outs[k], ins[k], stream=stream)
+        elif a.alg == "id_grad":
+            eng.inverse_dynamics_gradient_device(outs[k], ins[k], stream=stream)
+        elif a.alg == "fd":
+            eng.forward_dynamics_device(outs[k], ins[k], stream=stream)
+        elif a.alg == "minv":
+            eng.direct_minv_device(outs[k], ins[k], stream=stream)
+        else:
+            eng.inverse_dynamics_device(outs[k], ins[k], stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    # warm-up: W steps, then keep the GPU busy ~0.4 s so clocks settle and the sampler sees load
+    for i in range(a.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    t_warm = time.perf_counter()
+    i = a.warmup
+    while time.perf_counter() - t_warm < 0.4:
+        for _ in range(50):
+            step(i)
+            i += 1
+        torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream -----------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches_before = eng.launch_count()
+    t_lo = time.perf_counter()
+    e0.record(stream)
+    for i in range(a.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    t_hi = time.perf_counter()
+    gpu_launches = eng.launch_count() - launches_before
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / a.steps
+    value = world * N / (ms_per_step * 1e-3)
+    clocks = sampler.stop(t_lo - 0.3, t_hi + 0.05) if rank == 0 else None
+
+    # ---- end to end through the host API (pinned host buffers, H2D + kernel + D2H per step) --
+    data = eng.make_data(N)
+    data.h["q_qd_u"][:] = host_in
+    host_call = {"fd_grad": data.forward_dynamics_gradient, "id_grad": data.inverse_dynamics_gradient,
+                 "fd": data.forward_dynamics, "minv": data.direct_minv, "id": data.inverse_dynamics}[a.alg]
+    e2e_steps = max(3, min(a.steps, 20))
+    for _ in range(3):
+        host_call(N)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = host_call(N)
+        _ = float(res[0, 0])                     # the result is in host memory when the call returns
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * e2e_steps / float(te.item())
+    data.close()
+
+    # ---- N=128 latency (second half of the BASELINE metric), 1 GPU only ----------------------
+    lat = None
+    if rank == 0:
+        small_in, small_out = ins[0][:128], outs[0][:128]
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(300)]
+        for s, e in evs:
+            s.record(stream)
+            eng.forward_dynamics_gradient_device(small_out, small_in, num_timesteps=128, stride=3 * n, stream=stream) \
+                if a.alg == "fd_grad" else step(0)
+            e.record(stream)
+        torch.cuda.synchronize()
+        us = np.array([s.elapsed_time(e) * 1e3 for s, e in evs[50:]])
+        lat = {"p50_us": float(np.percentile(us, 50)), "p90_us": float(np.percentile(us, 90)),
+               "min_us": float(us.min()), "what": "%s N=128 single launch, CUDA events around the launch" % a.alg}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline ---------------------------------------------------------------------------
+    alg_flops = algorithmic_flops(robot)[a.alg]
+    alg_bytes = algorithmic_bytes(robot)[a.alg]
+    fp32_peak = eng.measure_fp32_tflops(5)
+    kernel_s = ms_per_step * 1e-3                      # one step == one launch of the dominant kernel
+    achieved = alg_flops * N / kernel_s / 1e12
+    traced = eng.traced_flops(a.alg)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {
+        "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+        "traffic": None,
+        "note": "FP32 SIMT (non-tensor) roofline; achieved = algorithmic flops/state (dense reference count, "
+                "SURVEY 8d) x states / launch time; peak = FFMA microbenchmark measured in this run "
+                "(theoretical %.1f)" % FP32_THEORETICAL_TFLOPS,
+        "algorithmic_flops_per_state": alg_flops, "traced_flops_per_state": traced,
+        "executed_tflops": traced * N / kernel_s / 1e12, "executed_frac": traced * N / kernel_s / 1e12 / fp32_peak,
+        "hbm": {"bound": "hbm", "achieved": alg_bytes * N / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes * N / kernel_s / 1e9 / hbm_peak,
+                "peak_source": "measured" if peaks else "fallback", "algorithmic_bytes_per_state": alg_bytes},
+    }
+
+    line = {
+        "metric": METRIC if (a.robot, a.alg, a.batch) == (ROBOT, ALG, BATCH) else "%s_evals_per_s_%s_N%d" % (a.alg, a.robot, N),
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s %s (forward-dynamics gradient), %d states per GPU, state-major [q|qd|u]" % (
+                       a.robot, a.alg, N),
+                   "states_per_gpu": N, "robot_hash": robot.param_hash(), "kernel": eng.kernel_kind(a.alg),
+                   "l2": "inputs/outputs rotate over %d buffer sets (%.0f MB > 126 MB L2)" % (nsets, nsets * set_bytes / 1e6)},
+        "clocks": clocks, "gpu_launches": int(gpu_launches),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * N * in_words,
+                "d2h_bytes_per_step": 4 * N * out_words, "steps": e2e_steps,
+                "what": "grid_forward_dynamics_gradient(grid_data*): pinned host in -> H2D -> kernel -> D2H -> pinned host out"},
+        "roofline": roofline, "latency_n128": lat,
+    }
+
+    if not a.no_cpu_baseline:
+        import multiprocessing as mp
+        cores = os.cpu_count() or 1
+        sample = a.cpu_sample or cores * 96
+        with mp.get_context("fork").Pool(cores) as pool:
+            cpu_reference_pass(a.robot, a.alg, cores * 4, cores, pool)
+            v, ms1, done = cpu_reference_pass(a.robot, a.alg, sample, cores, pool)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d seeded states over %d processes, oracle/rbd_numpy.py (port of reference "
+                                          "_test.py:496-520); single-core %.2f ms/eval" % (done, cores, ms1)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_b200_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,91 @@
+"""nvcc driver: robot -> generated .cu -> in-tree libgrid_<robot>_<hash>.so.
+
+Artefacts live under ``gridcodegenerator_b200/_generated/`` (sources) and
+``gridcodegenerator_b200/_lib/`` (shared objects); both are git-ignored but travel to
+the GPU box with the repo snapshot.  The cache key is robot hash + codegen version +
+hash of the static csrc/ and include/ files, so a stale library is never loaded.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import time
+from typing import Dict, Optional, Tuple
+
+from .codegen import CODEGEN_VERSION, KernelPlan, generate_translation_unit
+from .robot import Robot
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+INCLUDE = os.path.join(ROOT, "include")
+GEN_DIR = os.path.join(PKG, "_generated")
+LIB_DIR = os.path.join(PKG, "_lib")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _static_hash() -> str:
+    h = hashlib.sha256()
+    h.update(CODEGEN_VERSION.encode())
+    for d in (CSRC, INCLUDE):
+        for fn in sorted(os.listdir(d)):
+            if fn.endswith((".cuh", ".h", ".cu")):
+                with open(os.path.join(d, fn), "rb") as f:
+                    h.update(fn.encode())
+                    h.update(f.read())
+    for fn in ("codegen.py", "algorithms.py", "ir.py"):
+        with open(os.path.join(PKG, fn), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:10]
+
+
+def find_nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the B200 kernels cannot be built (there is no CPU fallback)")
+
+
+def lib_path(robot: Robot, tag: str = "") -> str:
+    return os.path.join(LIB_DIR, "libgrid_%s_%s_%s%s.so" % (robot.name, robot.param_hash(), _static_hash(), tag))
+
+
+def build_robot_library(robot: Robot, plan: Optional[KernelPlan] = None, force: bool = False, tag: str = "",
+                        verbose: bool = False, extra_flags=()) -> Tuple[str, Dict[str, dict]]:
+    """Returns (path to .so, build info).  Rebuilds only when the cache key changed."""
+    os.makedirs(GEN_DIR, exist_ok=True)
+    os.makedirs(LIB_DIR, exist_ok=True)
+    so = lib_path(robot, tag)
+    info: Dict[str, dict] = {}
+    if os.path.exists(so) and not force:
+        return so, info
+    t0 = time.time()
+    src, stats = generate_translation_unit(robot, plan)
+    cu = os.path.join(GEN_DIR, "grid_%s_%s%s.cu" % (robot.name, robot.param_hash(), tag))
+    with open(cu, "w") as f:
+        f.write(src)
+    t1 = time.time()
+    cmd = [find_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v", "-I", CSRC, "-I", INCLUDE, "-o", so + ".tmp", cu] + list(extra_flags)
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (cu, proc.stdout[-4000:], proc.stderr[-8000:]))
+    os.replace(so + ".tmp", so)
+    # drop stale libraries of the same robot
+    prefix = "libgrid_%s_" % robot.name
+    for fn in os.listdir(LIB_DIR):
+        if fn.startswith(prefix) and fn.endswith(tag + ".so") and os.path.join(LIB_DIR, fn) != so and not tag:
+            if "_" + _static_hash() not in fn or robot.param_hash() not in fn:
+                try:
+                    os.remove(os.path.join(LIB_DIR, fn))
+                except OSError:
+                    pass
+    info = {"stats": stats, "codegen_s": t1 - t0, "nvcc_s": time.time() - t1, "ptxas": proc.stderr}
+    with open(so[:-3] + ".ptxas.txt", "w") as f:
+        f.write(proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    return so, info

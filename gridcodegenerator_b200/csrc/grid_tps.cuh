@@ -1,0 +1,96 @@
+// grid_tps.cuh - thread-per-state launch shell around the traced straight-line programs.
+//
+// Replaces the reference's block-per-state kernels (e.g. algorithms/
+// _forward_dynamics_gradient.py:107-177: one CTA per knot point, ~111 __syncthreads per
+// state) for robots whose traced program fits one thread: every lane owns one state and
+// runs the robot-specialised straight-line code, so there are no barriers, shuffles,
+// atomics or topology lookups on the critical path.  A warp stages its 32 states through
+// shared memory so that global loads and stores are coalesced although the caller's layout
+// is state-major.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace gridb200 {
+
+constexpr int odd_pad(int words) { return words | 1; }   // odd stride => conflict-free lane access
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+template <class A>
+struct TpsShape {
+    static constexpr int IN = A::IN0 + A::IN1 + A::IN2;
+    static constexpr int IN_PAD = odd_pad(IN);
+    static constexpr int OUT_PAD = odd_pad(A::OUT);
+    static constexpr int WARP_WORDS = 32 * cmax(IN_PAD, OUT_PAD);   // input and output tiles alias
+};
+
+template <int WORDS, int PAD>
+__device__ __forceinline__ void tile_load(float *sw, int word_off, const float *__restrict__ g,
+                                          long long first_state, int stride, int cnt, int lane) {
+    if (WORDS == 0) return;
+    const float *src = g + first_state * (long long)stride;
+    if (stride == WORDS) {                      // contiguous tile: one coalesced sweep
+        for (int e = lane; e < cnt * WORDS; e += 32) {
+            int s = e / WORDS, k = e - s * WORDS;
+            sw[s * PAD + word_off + k] = __ldg(src + e);
+        }
+    } else {
+        for (int e = lane; e < cnt * WORDS; e += 32) {
+            int s = e / WORDS, k = e - s * WORDS;
+            sw[s * PAD + word_off + k] = __ldg(src + (long long)s * stride + k);
+        }
+    }
+}
+
+// One warp = one tile of 32 consecutive states; warps stride over tiles.
+template <class A, int WARPS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(32 * WARPS, MIN_BLOCKS)
+tps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0,
+           const float *__restrict__ d_in1, const float *__restrict__ d_in2, int num_states, float gravity) {
+    using S = TpsShape<A>;
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float *sw = smem + warp * S::WARP_WORDS;
+    const int ntiles = (num_states + 31) >> 5;
+    for (int tile = blockIdx.x * WARPS + warp; tile < ntiles; tile += gridDim.x * WARPS) {
+        const long long first = (long long)tile * 32;
+        const int cnt = min(32, num_states - (int)first);
+        tile_load<A::IN0, S::IN_PAD>(sw, 0, d_in0, first, stride0, cnt, lane);
+        tile_load<A::IN1, S::IN_PAD>(sw, A::IN0, d_in1, first, A::IN1, cnt, lane);
+        tile_load<A::IN2, S::IN_PAD>(sw, A::IN0 + A::IN1, d_in2, first, A::IN2, cnt, lane);
+        __syncwarp();
+        // lanes past the end of a ragged tile recompute the last valid state (results dropped)
+        const int src = min(lane, cnt - 1);
+        A::eval(sw + src * S::IN_PAD, sw + lane * S::OUT_PAD, gravity);
+        __syncwarp();
+        float *dst = d_out + first * A::OUT;
+        for (int e = lane; e < cnt * A::OUT; e += 32) {
+            int s = e / A::OUT, k = e - s * A::OUT;
+            dst[e] = sw[s * S::OUT_PAD + k];
+        }
+        __syncwarp();
+    }
+}
+
+template <class A, int WARPS, int MIN_BLOCKS>
+cudaError_t tps_launch(float *d_out, const float *d_in0, int stride0, const float *d_in1, const float *d_in2,
+                       int num_states, float gravity, cudaStream_t stream) {
+    using S = TpsShape<A>;
+    if (num_states <= 0) return cudaSuccess;
+    auto kern = tps_kernel<A, WARPS, MIN_BLOCKS>;
+    constexpr size_t smem_bytes = sizeof(float) * S::WARP_WORDS * WARPS;
+    static bool configured = false;             // benign race: idempotent attribute set
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int ntiles = (num_states + 31) / 32;
+    int blocks = (ntiles + WARPS - 1) / WARPS;
+    const int cap = 148 * 32;                   // beyond this, warps loop over tiles
+    if (blocks > cap) blocks = cap;
+    kern<<<blocks, 32 * WARPS, smem_bytes, stream>>>(d_out, d_in0, stride0, d_in1, d_in2, num_states, gravity);
+    return cudaGetLastError();
+}
+
+}  // namespace gridb200

@@ -1,0 +1,167 @@
+"""GPU parity proper: the CUDA path, called through the C ABI, against the oracle on seeded
+states and against the committed reference goldens."""
+import numpy as np
+import pytest
+
+from helpers import TOL, colmajor_batch, load_golden, relerr
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from gridcodegenerator_b200 import load_named_robot                      # noqa: E402
+from gridcodegenerator_b200.runtime import GridError, get_engine        # noqa: E402
+from gridcodegenerator_b200.synthetic import make_states, pack_q_qd, pack_q_qd_u, seed_for  # noqa: E402
+from oracle import rbd_numpy as O                                       # noqa: E402
+
+ALL = ("id", "minv", "fd", "id_grad", "fd_grad")
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def run_alg(eng, alg, q, qd, u, qdd=None, Minv=None, compressed=False):
+    n, N = eng.n, q.shape[0]
+    if alg == "id":
+        out = torch.empty(N, n, device="cuda")
+        eng.inverse_dynamics_device(out, dev(pack_q_qd(q, qd) if compressed else pack_q_qd_u(q, qd, u)),
+                                    None if qdd is None else dev(qdd))
+    elif alg == "minv":
+        out = torch.empty(N, n * n, device="cuda")
+        eng.direct_minv_device(out, dev(q if compressed else pack_q_qd_u(q, qd, u)))
+    elif alg == "fd":
+        out = torch.empty(N, n, device="cuda")
+        eng.forward_dynamics_device(out, dev(pack_q_qd_u(q, qd, u)))
+    elif alg == "id_grad":
+        out = torch.empty(N, 2 * n * n, device="cuda")
+        eng.inverse_dynamics_gradient_device(out, dev(pack_q_qd(q, qd) if compressed else pack_q_qd_u(q, qd, u)),
+                                             None if qdd is None else dev(qdd))
+    elif alg == "fd_grad":
+        out = torch.empty(N, 2 * n * n, device="cuda")
+        eng.forward_dynamics_gradient_device(out, dev(pack_q_qd_u(q, qd, u)),
+                                             None if qdd is None else dev(qdd), None if Minv is None else dev(Minv))
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def supported(eng, alg):
+    return eng.kernel_kind(alg) != "none"
+
+
+@pytest.mark.parametrize("tag", ["iiwa14", "iiwa14_damped", "hyq", "atlas", "chain64"])
+def test_against_reference_goldens(tag):
+    robot, z = load_golden(tag)
+    eng = get_engine(robot)
+    q, qd, u, qdd = z["q"], z["qd"], z["u"], z["qdd"]
+    checks = {
+        "id": [(dict(), z["c"]), (dict(qdd=qdd), z["c_qdd"])],
+        "minv": [(dict(), colmajor_batch(z["minv_upper"]))],
+        "fd": [(dict(), z["fd_qdd"])],
+        "id_grad": [(dict(), colmajor_batch(z["dc_du"])), (dict(qdd=qdd), colmajor_batch(z["dc_du_qdd"]))],
+        "fd_grad": [(dict(), colmajor_batch(z["df_du"]))],
+    }
+    ran = 0
+    for alg, cases in checks.items():
+        if not supported(eng, alg):
+            continue
+        for kw, ref in cases:
+            out = run_alg(eng, alg, q, qd, u, **kw)
+            assert relerr(out, ref) < TOL[alg], (tag, alg, relerr(out, ref))
+            ran += 1
+    assert ran > 0
+
+
+@pytest.mark.parametrize("name,N", [("iiwa14", 256), ("hyq", 256)])
+@pytest.mark.parametrize("alg", ALL)
+def test_against_oracle_256_states(name, N, alg):
+    robot = load_named_robot(name)
+    eng = get_engine(robot)
+    if not supported(eng, alg):
+        pytest.skip("no kernel for %s on %s yet" % (alg, name))
+    q, qd, u, qdd = make_states(robot.n, N, seed_for(name))
+    q64, qd64, u64 = (x.astype(np.float64) for x in (q, qd, u))
+    out = run_alg(eng, alg, q, qd, u)
+    ref = O.batch(robot, alg, q64, qd64, u64 if alg in ("fd", "fd_grad") else None)
+    assert relerr(out, ref) < TOL[alg], relerr(out, ref)
+    # per-state check too (a single bad state must not hide behind the tensor-wide max)
+    per = np.abs(out - ref).max(axis=1) / np.abs(ref).max(axis=1)
+    assert per.max() < 20 * TOL[alg], per.max()
+
+
+def test_qdd_minv_overload_and_compressed_layouts():
+    robot = load_named_robot("iiwa14")
+    eng = get_engine(robot)
+    n = robot.n
+    q, qd, u, qdd = make_states(n, 64, 99)
+    q64, qd64, qdd64 = (x.astype(np.float64) for x in (q, qd, qdd))
+    Mu = np.array([O.minv(robot, q64[s], dense=False).flatten(order="F") for s in range(64)], dtype=np.float32)
+    Md = np.array([O.minv(robot, q64[s]) for s in range(64)])
+    out = run_alg(eng, "fd_grad", q, qd, u, qdd=qdd, Minv=Mu)
+    ref = O.batch(robot, "fd_grad_qdd_minv", q64, qd64, qdd64, Minv_in=Md)
+    assert relerr(out, ref) < TOL["fd_grad"]
+    # USE_COMPRESSED_MEM strides give the same answers as the 3n stride
+    for alg in ("id", "minv", "id_grad"):
+        a = run_alg(eng, alg, q, qd, u)
+        b = run_alg(eng, alg, q, qd, u, compressed=True)
+        assert np.array_equal(a, b), alg
+
+
+@pytest.mark.parametrize("N", [0, 1, 31, 32, 33, 1000])
+def test_ragged_and_empty_batches(N):
+    robot = load_named_robot("iiwa14")
+    eng = get_engine(robot)
+    n = robot.n
+    q, qd, u, _ = make_states(n, max(N, 1), 5)
+    q, qd, u = q[:N], qd[:N], u[:N]
+    big = run_alg(eng, "fd_grad", *make_states(n, 1000, 5)[:3])
+    guard = torch.full((N + 2, 2 * n * n), 7.0, device="cuda")
+    if N:
+        eng.forward_dynamics_gradient_device(guard[1:N + 1], dev(pack_q_qd_u(q, qd, u)), num_timesteps=N, stride=3 * n)
+    else:
+        eng.forward_dynamics_gradient_device(guard[1:1], torch.empty(0, 3 * n, device="cuda"), num_timesteps=0, stride=3 * n)
+    torch.cuda.synchronize()
+    g = guard.cpu().numpy()
+    assert np.all(g[0] == 7.0) and np.all(g[-1] == 7.0)        # no out-of-bounds writes
+    assert np.array_equal(g[1:N + 1], big[:N])                  # batch size does not change results
+
+
+def test_full_size_properties_iiwa_65536():
+    """BASELINE size: checks that do not need the oracle at every state - Minv symmetry via
+    M*Minv = I on a sample, FD/ID round trip, and fd_grad consistency between overloads."""
+    robot = load_named_robot("iiwa14")
+    eng = get_engine(robot)
+    n, N = robot.n, 65536
+    q, qd, u, _ = make_states(n, N, seed_for("iiwa14"))
+    qdd = run_alg(eng, "fd", q, qd, u)
+    tau = run_alg(eng, "id", q, qd, u, qdd=qdd)                 # ID(FD(u)) == u
+    assert relerr(tau, u) < 1e-3
+    assert np.isfinite(qdd).all()
+    Minv = run_alg(eng, "minv", q, qd, u)
+    a = run_alg(eng, "fd_grad", q, qd, u)
+    b = run_alg(eng, "fd_grad", q, qd, u, qdd=qdd, Minv=Minv)   # same result from precomputed qdd, Minv
+    assert relerr(b, a) < 1e-3
+    idx = np.random.default_rng(0).choice(N, 64, replace=False)
+    ref = O.batch(robot, "fd_grad", q[idx].astype(np.float64), qd[idx].astype(np.float64), u[idx].astype(np.float64))
+    assert relerr(a[idx], ref) < TOL["fd_grad"]
+
+
+def test_host_path_grid_data():
+    robot = load_named_robot("iiwa14")
+    eng = get_engine(robot)
+    n, N = robot.n, 5000
+    q, qd, u, qdd = make_states(n, N, 17)
+    data = eng.make_data(N)
+    data.h["q_qd_u"][:] = pack_q_qd_u(q, qd, u)
+    df = data.forward_dynamics_gradient(N).copy()
+    assert np.array_equal(df, run_alg(eng, "fd_grad", q, qd, u))
+    c = data.inverse_dynamics(N).copy()
+    assert np.array_equal(c, run_alg(eng, "id", q, qd, u))
+    data.h["qdd"][:] = qdd
+    c2 = data.inverse_dynamics(N, use_qdd=True).copy()
+    assert np.array_equal(c2, run_alg(eng, "id", q, qd, u, qdd=qdd))
+    assert np.array_equal(data.direct_minv(N).copy(), run_alg(eng, "minv", q, qd, u))
+    assert np.array_equal(data.forward_dynamics(N).copy(), run_alg(eng, "fd", q, qd, u))
+    assert np.array_equal(data.inverse_dynamics_gradient(N).copy(), run_alg(eng, "id_grad", q, qd, u))
+    with pytest.raises(GridError):
+        data.forward_dynamics(N + 1)
+    data.close()

@@ -1,0 +1,80 @@
+"""The numpy oracle against the reference's own outputs (committed goldens, and the live
+reference when /root/reference exists in this container)."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import load_golden, relerr
+from oracle import rbd_numpy as O
+
+TAGS = ["iiwa14", "iiwa14_damped", "hyq", "atlas", "chain64"]
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_oracle_matches_reference_goldens(tag):
+    robot, z = load_golden(tag)
+    q, qd, u, qdd = (z[k].astype(np.float64) for k in ("q", "qd", "u", "qdd"))
+    N = q.shape[0]
+    for s in range(N):
+        assert relerr(O.rnea(robot, q[s], qd[s])[0], z["c"][s]) < 1e-12
+        assert relerr(O.rnea(robot, q[s], qd[s], qdd[s])[0], z["c_qdd"][s]) < 1e-12
+        assert relerr(O.minv(robot, q[s]), z["minv_dense"][s]) < 1e-11
+        assert relerr(O.minv(robot, q[s], dense=False), z["minv_upper"][s]) < 1e-11
+        assert relerr(O.fd(robot, q[s], qd[s], u[s]), z["fd_qdd"][s]) < 1e-10
+        assert relerr(O.rnea_grad(robot, q[s], qd[s]), z["dc_du"][s]) < 1e-11
+        assert relerr(O.rnea_grad(robot, q[s], qd[s], qdd[s]), z["dc_du_qdd"][s]) < 1e-11
+        if s < 2:
+            assert relerr(O.fd_grad(robot, q[s], qd[s], u[s]), z["df_du"][s]) < 1e-9
+
+
+def test_minv_upper_is_triangular_and_dense_is_symmetric():
+    robot, z = load_golden("hyq")
+    Mu = O.minv(robot, z["q"][0].astype(np.float64), dense=False)
+    assert np.all(np.tril(Mu, -1) == 0)
+    Md = O.minv(robot, z["q"][0].astype(np.float64))
+    assert np.allclose(Md, Md.T)
+
+
+@pytest.mark.parametrize("name", ["iiwa14", "hyq", "atlas"])
+def test_oracle_invariants(name):
+    """M * Minv = I with M from RNEA unit accelerations (gravity 0), and central finite
+    differences for both gradients."""
+    robot, z = load_golden(name)
+    n = robot.n
+    q, qd, u = (z[k][0].astype(np.float64) for k in ("q", "qd", "u"))
+    M = np.zeros((n, n))
+    for j in range(n):
+        e = np.zeros(n)
+        e[j] = 1.0
+        M[:, j] = O.rnea(robot, q, np.zeros(n), e, gravity=0.0)[0]
+    assert np.abs(O.minv(robot, q) @ M - np.eye(n)).max() < 1e-9
+    eps = 1e-6
+    num = np.zeros((n, 2 * n))
+    for j in range(n):
+        d = np.zeros(n)
+        d[j] = eps
+        num[:, j] = (O.fd(robot, q + d, qd, u) - O.fd(robot, q - d, qd, u)) / (2 * eps)
+        num[:, n + j] = (O.fd(robot, q, qd + d, u) - O.fd(robot, q, qd - d, u)) / (2 * eps)
+    assert relerr(O.fd_grad(robot, q, qd, u), num) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/_test.py"), reason="reference tree not present")
+@pytest.mark.parametrize("name", ["iiwa14", "hyq"])
+def test_oracle_matches_live_reference(name):
+    sys.path.insert(0, "/root")
+    from reference import GRiDCodeGenerator as RefGen
+    robot, _ = load_golden(name)
+    robot = robot.with_damping(0.25)
+    g = RefGen(robot)
+    rng = np.random.default_rng(7)
+    n = robot.n
+    q, qd, u = rng.uniform(-3, 3, n), rng.uniform(-2, 2, n), rng.uniform(-20, 20, n)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = g.test_fd_grad(q, qd, u)
+        ref_dc = g.test_rnea_grad(q, qd)
+    assert relerr(O.fd_grad(robot, q, qd, u), ref) < 1e-10
+    assert relerr(O.rnea_grad(robot, q, qd), ref_dc) < 1e-11

@@ -1,0 +1,83 @@
+"""Host logic: the traced per-robot programs (numpy interpretation of the same DAG the CUDA
+emitter prints) against the oracle, in float64 and float32."""
+import numpy as np
+import pytest
+
+from gridcodegenerator_b200 import load_named_robot
+from gridcodegenerator_b200.algorithms import TRACERS, algorithmic_flops
+from gridcodegenerator_b200.synthetic import make_states
+from helpers import TOL, relerr
+from oracle import rbd_numpy as O
+
+
+def _ins(**kw):
+    d = {"gravity": 9.81}
+    for k, v in kw.items():
+        for i in range(v.shape[1]):
+            d["%s%d" % (k, i)] = v[:, i]
+    return d
+
+
+def _run(robot, key, q, qd, u, qdd, dtype):
+    p = TRACERS[key](robot)
+    N = q.shape[0]
+    if key == "id":
+        return p.evaluate(_ins(q=q, qd=qd), dtype)["c"], O.batch(robot, "id", q, qd), "id"
+    if key == "id_qdd":
+        return p.evaluate(_ins(q=q, qd=qd, qdd=qdd), dtype)["c"], O.batch(robot, "id", q, qd, qdd), "id"
+    if key == "minv":
+        return p.evaluate(_ins(q=q), dtype)["Minv"], O.batch(robot, "minv", q), "minv"
+    if key == "fd":
+        return p.evaluate(_ins(q=q, qd=qd, u=u), dtype)["qdd"], O.batch(robot, "fd", q, qd, u), "fd"
+    if key == "id_grad":
+        return p.evaluate(_ins(q=q, qd=qd), dtype)["dc_du"], O.batch(robot, "id_grad", q, qd), "id_grad"
+    if key == "id_grad_qdd":
+        return p.evaluate(_ins(q=q, qd=qd, qdd=qdd), dtype)["dc_du"], O.batch(robot, "id_grad", q, qd, qdd), "id_grad"
+    if key == "fd_grad":
+        return p.evaluate(_ins(q=q, qd=qd, u=u), dtype)["df_du"], O.batch(robot, "fd_grad", q, qd, u), "fd_grad"
+    if key == "fd_grad_qdd_minv":
+        Mu = np.array([O.minv(robot, q[s], dense=False).flatten(order="F") for s in range(N)])
+        Md = np.array([O.minv(robot, q[s]) for s in range(N)])
+        return (p.evaluate(_ins(q=q, qd=qd, qdd=qdd, Minv=Mu), dtype)["df_du"],
+                O.batch(robot, "fd_grad_qdd_minv", q, qd, qdd, Minv_in=Md), "fd_grad")
+    raise KeyError(key)
+
+
+@pytest.mark.parametrize("name", ["iiwa14", "hyq"])
+@pytest.mark.parametrize("key", list(TRACERS))
+def test_traced_program_matches_oracle(name, key):
+    robot = load_named_robot(name).with_damping(0.3)
+    q, qd, u, qdd = (x.astype(np.float64) for x in make_states(robot.n, 4, 11))
+    out, ref, alg = _run(robot, key, q, qd, u, qdd, np.float64)
+    assert relerr(out, ref) < 1e-11
+    out32, _, _ = _run(robot, key, q, qd, u, qdd, np.float32)
+    assert relerr(out32, ref) < TOL[alg]
+
+
+@pytest.mark.parametrize("name", ["atlas", "chain64"])
+def test_traced_id_large_robots(name):
+    robot = load_named_robot(name)
+    q, qd, u, qdd = (x.astype(np.float64) for x in make_states(robot.n, 2, 3))
+    out, ref, _ = _run(robot, "id_qdd", q, qd, u, qdd, np.float64)
+    assert relerr(out, ref) < 1e-11
+
+
+def test_traced_work_is_below_dense_reference_count():
+    robot = load_named_robot("iiwa14")
+    alg = algorithmic_flops(robot)
+    assert alg["fd_grad"] == 41834 and alg["id"] == 2779
+    traced = TRACERS["fd_grad"](robot).op_counts()["flops"]
+    assert traced < alg["fd_grad"] / 3
+
+
+def test_prismatic_joint_traces():
+    """A prismatic joint makes r (not E) depend on q."""
+    from gridcodegenerator_b200.robot import Robot, spatial_inertia
+    I = spatial_inertia(2.0, [0.01, 0.02, 0.03], np.diag([0.1, 0.2, 0.3]))
+    E = np.eye(3)
+    robot = Robot("pr", [-1, 0, 1], [2, 4, 0], [E, E, E], [[0, 0, 0.1], [0.2, 0, 0], [0, 0.3, 0]], [I, I, I],
+                  [0.1, 0.0, 0.2])
+    q, qd, u, qdd = (x.astype(np.float64) for x in make_states(3, 3, 5))
+    for key in TRACERS:
+        out, ref, _ = _run(robot, key, q, qd, u, qdd, np.float64)
+        assert relerr(out, ref) < 1e-11, key
