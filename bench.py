@@ -39,6 +39,8 @@ def parse_args():
     ap.add_argument("--alg", default=ALG)
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="minimal run for ncu: W+K launches only, no extended warm-up, e2e, latency or CPU legs")
     ap.add_argument("--cpu-sample", type=int, default=0, help="states in the CPU baseline sample (0 = auto)")
     return ap.parse_args()
 
@@ -206,7 +208,7 @@ def run_b200_arm(a):
     torch.cuda.synchronize()
     t_warm = time.perf_counter()
     i = a.warmup
-    while time.perf_counter() - t_warm < 0.4:
+    while not a.profile and time.perf_counter() - t_warm < 0.4:
         for _ in range(50):
             step(i)
             i += 1
@@ -232,6 +234,11 @@ def run_b200_arm(a):
     ms_per_step = ms_total / a.steps
     value = world * N / (ms_per_step * 1e-3)
     clocks = sampler.stop(t_lo - 0.3, t_hi + 0.05) if rank == 0 else None
+
+    if a.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_per_step, "gpu_launches": int(gpu_launches)}))
+        return
 
     # ---- end to end through the host API (pinned host buffers, H2D + kernel + D2H per step) --
     data = eng.make_data(N)

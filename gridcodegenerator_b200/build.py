@@ -25,7 +25,7 @@ GEN_DIR = os.path.join(PKG, "_generated")
 LIB_DIR = os.path.join(PKG, "_lib")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-gnu-unique", "-shared"]
 
 
 def _static_hash() -> str:
@@ -64,7 +64,7 @@ def build_robot_library(robot: Robot, plan: Optional[KernelPlan] = None, force: 
     if os.path.exists(so) and not force:
         return so, info
     t0 = time.time()
-    src, stats = generate_translation_unit(robot, plan)
+    src, stats = generate_translation_unit(robot, plan, ns_tag=tag)
     cu = os.path.join(GEN_DIR, "grid_%s_%s%s.cu" % (robot.name, robot.param_hash(), tag))
     with open(cu, "w") as f:
         f.write(src)

@@ -45,7 +45,7 @@ def _flit(x: float) -> str:
 
 
 def emit_eval(p: Program, n: int, in0_words: int, in1_words: int, out_name: str, out_words: int,
-              indent: str = "        ") -> Tuple[List[str], Dict[str, int]]:
+              indent: str = "        ", sync_every: int = 0) -> Tuple[List[str], Dict[str, int]]:
     """Prints the live part of ``p`` as straight-line CUDA.  Stores are emitted at the
     point in the trace where the algorithm produced them, so finished output columns do
     not occupy registers."""
@@ -87,10 +87,14 @@ def emit_eval(p: Program, n: int, in0_words: int, in1_words: int, out_name: str,
     lines.append(indent + "__syncwarp();")
     for idx, v in outs_by_pos.get(-1, []):
         body.append("%ss_out[%d] = %s;" % (indent, idx, _flit(v.c)))
+    emitted = 0
     for i, k in enumerate(p.nodes):
         if not live[i]:
             continue
         op = k[0]
+        emitted += 1
+        if sync_every and emitted % sync_every == 0:
+            body.append(indent + "__syncthreads();")
         if op == "in":
             if k[1] == "gravity":
                 body.append("%sconst float t%d = gravity;" % (indent, i))
@@ -117,18 +121,18 @@ def emit_eval(p: Program, n: int, in0_words: int, in1_words: int, out_name: str,
     return lines + body, p.op_counts()
 
 
-def emit_alg_struct(robot: Robot, variant: str, p: Optional[Program] = None) -> Tuple[str, Dict[str, int]]:
+def emit_alg_struct(robot: Robot, variant: str, p: Optional[Program] = None,
+                    sync_every: int = 0) -> Tuple[str, Dict[str, int]]:
     n = robot.n
     sname, m0, m1, m2, out_name, out_fn = VARIANTS[variant]
     in0, in1, in2, out = m0 * n, m1 * n, m2 * n * n, out_fn(n)
     p = p if p is not None else TRACERS[variant](robot)
-    body, cnt = emit_eval(p, n, in0, in1, out_name, out)
+    body, cnt = emit_eval(p, n, in0, in1, out_name, out, sync_every=sync_every)
     txt = ["struct %s {" % sname,
            "    static constexpr int IN0 = %d, IN1 = %d, IN2 = %d, OUT = %d;" % (in0, in1, in2, out),
            "    static constexpr long long TRACED_FLOPS = %d;   // %d mul + %d add per state" % (
                cnt["flops"], cnt["mul"], cnt["add"]),
-           "    static __device__ __forceinline__ void eval(const float *__restrict__ s_in, float *__restrict__ s_out,"
-           " const float gravity) {"]
+           "    static __device__ __forceinline__ void eval(const float *s_in, float *s_out, const float gravity) {"]
     txt += body
     txt += ["    }", "};", ""]
     return "\n".join(txt), cnt
@@ -138,21 +142,25 @@ class KernelPlan:
     """Which kernel family serves each algorithm of a robot, and its launch shape."""
 
     def __init__(self, robot: Robot, tps_max_flops: int = 60000, tps_warps: int = 1,
-                 tps_min_blocks: Optional[Dict[str, int]] = None):
+                 tps_min_blocks: Optional[Dict[str, int]] = None, tps_sync_every: int = 0):
         self.robot = robot
         self.tps_warps = tps_warps
+        self.tps_sync_every = tps_sync_every if tps_warps > 1 else 0
         alg = algorithmic_flops(robot)
         self.kind: Dict[str, str] = {}
         for a in ("id", "minv", "fd", "id_grad", "fd_grad"):
             # the dense reference count over-states traced work by ~4x; gate on it
             self.kind[a] = "tps" if alg[a] <= tps_max_flops else "none"
-        self.min_blocks = {"id": 16, "minv": 16, "fd": 16, "id_grad": 16, "fd_grad": 16}
+        # resident single-warp CTAs per SM = register cap 65536/(32*min_blocks).  Measured on B200
+        # (profiles/r1_sweep_tps.md): the gradient programs spill at 128/168 registers and run
+        # 2.1x faster at 255 registers with no spills; the small programs fit 128.
+        self.min_blocks = {"id": 16, "minv": 16, "fd": 16, "id_grad": 8, "fd_grad": 8}
         if tps_min_blocks:
             self.min_blocks.update(tps_min_blocks)
 
 
 _LAUNCHERS = r'''
-namespace gridb200 { namespace gen {
+namespace GRID_NS { namespace gen {
 %(launchers)s
 const char *kernel_kind(const char *alg) {
     if (!alg) return "none";
@@ -164,31 +172,36 @@ long long traced_flops(const char *alg) {
 %(flops)s
     return 0;
 }
-}}  // namespace gridb200::gen
+}}  // namespace GRID_NS::gen
 '''
 
 
-def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None) -> Tuple[str, Dict[str, dict]]:
+def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
+                              ns_tag: str = "") -> Tuple[str, Dict[str, dict]]:
     plan = plan or KernelPlan(robot)
+    ns_tag = re.sub(r"\W", "_", ns_tag)
     n = robot.n
     out: List[str] = []
     stats: Dict[str, dict] = {}
     out.append("// GENERATED by gridcodegenerator_b200.codegen v%s for robot '%s' (hash %s) - do not edit.\n"
                % (CODEGEN_VERSION, robot.name, robot.param_hash()))
+    # a robot-unique namespace: several robot libraries are loaded into one process and C++
+    # vague-linkage symbols (template statics) would otherwise be shared between them
+    out.append("#define GRID_NS grid_%s_%s%s\n" % (re.sub(r"\W", "_", robot.name), robot.param_hash(), ns_tag))
     out.append('#include <cuda_runtime.h>\n#include "grid_tps.cuh"\n')
     out.append('#define GRID_ROBOT_NAME "%s"\n#define GRID_ROBOT_HASH "%s"\n#define GRID_N %d\n'
                % (robot.name, robot.param_hash(), n))
-    out.append("namespace gridb200 { namespace gen {\n")
+    out.append("namespace GRID_NS { namespace gen {\n")
     needed = {"id": ("id", "id_qdd"), "minv": ("minv",), "fd": ("fd",), "id_grad": ("id_grad", "id_grad_qdd"),
               "fd_grad": ("fd_grad", "fd_grad_qdd_minv")}
     for a, variants in needed.items():
         if plan.kind[a] != "tps":
             continue
         for v in variants:
-            txt, cnt = emit_alg_struct(robot, v)
+            txt, cnt = emit_alg_struct(robot, v, sync_every=plan.tps_sync_every)
             out.append(txt)
             stats[v] = cnt
-    out.append("}}  // namespace gridb200::gen\n")
+    out.append("}}  // namespace GRID_NS::gen\n")
 
     W = plan.tps_warps
 

@@ -2,8 +2,8 @@
 //
 // The generated translation unit defines, before including this file:
 //   GRID_ROBOT_NAME, GRID_ROBOT_HASH, GRID_N
-//   gridb200::gen::launch_id / launch_minv / launch_fd / launch_id_grad / launch_fd_grad
-//   gridb200::gen::kernel_kind(alg), gridb200::gen::traced_flops(alg)
+//   GRID_NS::gen::launch_id / launch_minv / launch_fd / launch_id_grad / launch_fd_grad
+//   GRID_NS::gen::kernel_kind(alg), GRID_NS::gen::traced_flops(alg)
 // Host-side structure mirrors the reference's emitted host layer
 // (GRiDCodeGenerator.py:87-203 gridData/init_gridData/init_grid/close_grid and the
 // *_host generators, e.g. algorithms/_forward_dynamics_gradient.py:179-242) with three
@@ -18,7 +18,7 @@
 
 #include "grid_b200.h"
 
-namespace gridb200 {
+namespace GRID_NS {
 
 static thread_local std::string g_last_error;
 static std::atomic<long long> g_launches{0};
@@ -42,13 +42,13 @@ static int check_args(const void *out, const void *in, int stride, int min_strid
 constexpr int kStreams = 4;
 constexpr int kMinChunk = 2048;      // states; below this, pipelining costs more than it hides
 
-}  // namespace gridb200
+}  // namespace GRID_NS
 
 struct grid_data {
     int cap;
     float *h_q_qd_u, *h_q_qd, *h_q, *h_c, *h_Minv, *h_qdd, *h_dc_du, *h_df_du;
     float *d_q_qd_u, *d_q_qd, *d_q, *d_c, *d_Minv, *d_qdd, *d_dc_du, *d_df_du;
-    cudaStream_t streams[gridb200::kStreams];
+    cudaStream_t streams[GRID_NS::kStreams];
 };
 
 extern "C" {
@@ -57,49 +57,49 @@ int grid_abi_version(void) { return GRID_B200_ABI_VERSION; }
 int grid_num_joints(void) { return GRID_N; }
 const char *grid_robot_name(void) { return GRID_ROBOT_NAME; }
 const char *grid_robot_hash(void) { return GRID_ROBOT_HASH; }
-const char *grid_last_error(void) { return gridb200::g_last_error.c_str(); }
-const char *grid_kernel_kind(const char *alg) { return gridb200::gen::kernel_kind(alg); }
-long long grid_traced_flops(const char *alg) { return gridb200::gen::traced_flops(alg); }
-long long grid_launch_count(void) { return gridb200::g_launches.load(); }
+const char *grid_last_error(void) { return GRID_NS::g_last_error.c_str(); }
+const char *grid_kernel_kind(const char *alg) { return GRID_NS::gen::kernel_kind(alg); }
+long long grid_traced_flops(const char *alg) { return GRID_NS::gen::traced_flops(alg); }
+long long grid_launch_count(void) { return GRID_NS::g_launches.load(); }
 
 #define GRID_LAUNCH(expr, name)                                         \
     do {                                                                \
         cudaError_t e__ = (expr);                                       \
-        if (e__ != cudaSuccess) return gridb200::fail(name, e__);       \
-        gridb200::g_launches.fetch_add(1);                              \
+        if (e__ != cudaSuccess) return GRID_NS::fail(name, e__);       \
+        GRID_NS::g_launches.fetch_add(1);                              \
     } while (0)
 
 int grid_inverse_dynamics_device(float *d_c, const float *d_q_qd, int stride, const float *d_qdd,
                                  int num_timesteps, float gravity, void *stream) {
-    if (int rc = gridb200::check_args(d_c, d_q_qd, stride, 2 * GRID_N, num_timesteps)) return rc;
+    if (int rc = GRID_NS::check_args(d_c, d_q_qd, stride, 2 * GRID_N, num_timesteps)) return rc;
     if (num_timesteps == 0) return 0;
-    GRID_LAUNCH(gridb200::gen::launch_id(d_c, d_q_qd, stride, d_qdd, num_timesteps, gravity, (cudaStream_t)stream),
+    GRID_LAUNCH(GRID_NS::gen::launch_id(d_c, d_q_qd, stride, d_qdd, num_timesteps, gravity, (cudaStream_t)stream),
                 "inverse_dynamics_kernel");
     return 0;
 }
 
 int grid_direct_minv_device(float *d_Minv, const float *d_q, int stride, int num_timesteps, void *stream) {
-    if (int rc = gridb200::check_args(d_Minv, d_q, stride, GRID_N, num_timesteps)) return rc;
+    if (int rc = GRID_NS::check_args(d_Minv, d_q, stride, GRID_N, num_timesteps)) return rc;
     if (num_timesteps == 0) return 0;
-    GRID_LAUNCH(gridb200::gen::launch_minv(d_Minv, d_q, stride, num_timesteps, (cudaStream_t)stream),
+    GRID_LAUNCH(GRID_NS::gen::launch_minv(d_Minv, d_q, stride, num_timesteps, (cudaStream_t)stream),
                 "direct_minv_kernel");
     return 0;
 }
 
 int grid_forward_dynamics_device(float *d_qdd, const float *d_q_qd_u, int stride, int num_timesteps,
                                  float gravity, void *stream) {
-    if (int rc = gridb200::check_args(d_qdd, d_q_qd_u, stride, 3 * GRID_N, num_timesteps)) return rc;
+    if (int rc = GRID_NS::check_args(d_qdd, d_q_qd_u, stride, 3 * GRID_N, num_timesteps)) return rc;
     if (num_timesteps == 0) return 0;
-    GRID_LAUNCH(gridb200::gen::launch_fd(d_qdd, d_q_qd_u, stride, num_timesteps, gravity, (cudaStream_t)stream),
+    GRID_LAUNCH(GRID_NS::gen::launch_fd(d_qdd, d_q_qd_u, stride, num_timesteps, gravity, (cudaStream_t)stream),
                 "forward_dynamics_kernel");
     return 0;
 }
 
 int grid_inverse_dynamics_gradient_device(float *d_dc_du, const float *d_q_qd, int stride, const float *d_qdd,
                                           int num_timesteps, float gravity, void *stream) {
-    if (int rc = gridb200::check_args(d_dc_du, d_q_qd, stride, 2 * GRID_N, num_timesteps)) return rc;
+    if (int rc = GRID_NS::check_args(d_dc_du, d_q_qd, stride, 2 * GRID_N, num_timesteps)) return rc;
     if (num_timesteps == 0) return 0;
-    GRID_LAUNCH(gridb200::gen::launch_id_grad(d_dc_du, d_q_qd, stride, d_qdd, num_timesteps, gravity,
+    GRID_LAUNCH(GRID_NS::gen::launch_id_grad(d_dc_du, d_q_qd, stride, d_qdd, num_timesteps, gravity,
                                               (cudaStream_t)stream),
                 "inverse_dynamics_gradient_kernel");
     return 0;
@@ -108,10 +108,10 @@ int grid_inverse_dynamics_gradient_device(float *d_dc_du, const float *d_q_qd, i
 int grid_forward_dynamics_gradient_device(float *d_df_du, const float *d_q_qd_u, int stride, const float *d_qdd,
                                           const float *d_Minv, int num_timesteps, float gravity, void *stream) {
     const bool pre = d_qdd != nullptr || d_Minv != nullptr;
-    if (pre && !(d_qdd && d_Minv)) return gridb200::fail_msg("d_qdd and d_Minv must both be given or both be NULL");
-    if (int rc = gridb200::check_args(d_df_du, d_q_qd_u, stride, (pre ? 2 : 3) * GRID_N, num_timesteps)) return rc;
+    if (pre && !(d_qdd && d_Minv)) return GRID_NS::fail_msg("d_qdd and d_Minv must both be given or both be NULL");
+    if (int rc = GRID_NS::check_args(d_df_du, d_q_qd_u, stride, (pre ? 2 : 3) * GRID_N, num_timesteps)) return rc;
     if (num_timesteps == 0) return 0;
-    GRID_LAUNCH(gridb200::gen::launch_fd_grad(d_df_du, d_q_qd_u, stride, d_qdd, d_Minv, num_timesteps, gravity,
+    GRID_LAUNCH(GRID_NS::gen::launch_fd_grad(d_df_du, d_q_qd_u, stride, d_qdd, d_Minv, num_timesteps, gravity,
                                               (cudaStream_t)stream),
                 "forward_dynamics_gradient_kernel");
     return 0;
@@ -121,7 +121,7 @@ int grid_forward_dynamics_gradient_device(float *d_df_du, const float *d_q_qd_u,
 #define GRID_CU(expr, where)                                            \
     do {                                                                \
         cudaError_t e__ = (expr);                                       \
-        if (e__ != cudaSuccess) return gridb200::fail(where, e__);      \
+        if (e__ != cudaSuccess) return GRID_NS::fail(where, e__);      \
     } while (0)
 
 static int grid_data_alloc(grid_data *hd, int T) {
@@ -137,23 +137,23 @@ static int grid_data_alloc(grid_data *hd, int T) {
     }
     int lo = 0, hi = 0;
     GRID_CU(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange");
-    for (int i = 0; i < gridb200::kStreams; i++)
+    for (int i = 0; i < GRID_NS::kStreams; i++)
         GRID_CU(cudaStreamCreateWithPriority(&hd->streams[i], cudaStreamNonBlocking, hi), "cudaStreamCreate");
     return 0;
 }
 
 grid_data *grid_data_create(int max_timesteps) {
     if (max_timesteps <= 0) {
-        gridb200::fail_msg("max_timesteps must be positive");
+        GRID_NS::fail_msg("max_timesteps must be positive");
         return nullptr;
     }
     grid_data *hd = new grid_data();
     memset(hd, 0, sizeof(*hd));
     hd->cap = max_timesteps;
     if (grid_data_alloc(hd, max_timesteps) != 0) {
-        std::string keep = gridb200::g_last_error;
+        std::string keep = GRID_NS::g_last_error;
         grid_data_destroy(hd);
-        gridb200::g_last_error = keep;
+        GRID_NS::g_last_error = keep;
         return nullptr;
     }
     return hd;
@@ -184,7 +184,7 @@ float *grid_data_ptr(grid_data *hd, const char *field) {
 
 }  // extern "C"
 
-namespace gridb200 {
+namespace GRID_NS {
 
 struct Span { const float *h; float *d; size_t words; };          // per-state words of an input
 struct OutSpan { float *h; float *d; size_t words; };
@@ -214,17 +214,17 @@ static int run_pipelined(grid_data *hd, int T, const Span *ins, int n_ins, OutSp
     return 0;
 }
 
-}  // namespace gridb200
+}  // namespace GRID_NS
 
 extern "C" {
 
 int grid_inverse_dynamics(grid_data *hd, int T, float gravity, int use_qdd, int compressed) {
-    if (!hd) return gridb200::fail_msg("null grid_data");
+    if (!hd) return GRID_NS::fail_msg("null grid_data");
     const size_t n = GRID_N, st = compressed ? 2 * n : 3 * n;
-    gridb200::Span ins[2] = {{compressed ? hd->h_q_qd : hd->h_q_qd_u, compressed ? hd->d_q_qd : hd->d_q_qd_u, st},
+    GRID_NS::Span ins[2] = {{compressed ? hd->h_q_qd : hd->h_q_qd_u, compressed ? hd->d_q_qd : hd->d_q_qd_u, st},
                              {hd->h_qdd, hd->d_qdd, n}};
     float *d_in = ins[0].d;
-    return gridb200::run_pipelined(hd, T, ins, use_qdd ? 2 : 1, {hd->h_c, hd->d_c, n},
+    return GRID_NS::run_pipelined(hd, T, ins, use_qdd ? 2 : 1, {hd->h_c, hd->d_c, n},
         [&](size_t first, int cnt, cudaStream_t s) {
             return grid_inverse_dynamics_device(hd->d_c + first * n, d_in + first * st, (int)st,
                                                 use_qdd ? hd->d_qdd + first * n : nullptr, cnt, gravity, s);
@@ -232,21 +232,21 @@ int grid_inverse_dynamics(grid_data *hd, int T, float gravity, int use_qdd, int 
 }
 
 int grid_direct_minv(grid_data *hd, int T, int compressed) {
-    if (!hd) return gridb200::fail_msg("null grid_data");
+    if (!hd) return GRID_NS::fail_msg("null grid_data");
     const size_t n = GRID_N, st = compressed ? n : 3 * n;
-    gridb200::Span ins[1] = {{compressed ? hd->h_q : hd->h_q_qd_u, compressed ? hd->d_q : hd->d_q_qd_u, st}};
+    GRID_NS::Span ins[1] = {{compressed ? hd->h_q : hd->h_q_qd_u, compressed ? hd->d_q : hd->d_q_qd_u, st}};
     float *d_in = ins[0].d;
-    return gridb200::run_pipelined(hd, T, ins, 1, {hd->h_Minv, hd->d_Minv, n * n},
+    return GRID_NS::run_pipelined(hd, T, ins, 1, {hd->h_Minv, hd->d_Minv, n * n},
         [&](size_t first, int cnt, cudaStream_t s) {
             return grid_direct_minv_device(hd->d_Minv + first * n * n, d_in + first * st, (int)st, cnt, s);
         });
 }
 
 int grid_forward_dynamics(grid_data *hd, int T, float gravity) {
-    if (!hd) return gridb200::fail_msg("null grid_data");
+    if (!hd) return GRID_NS::fail_msg("null grid_data");
     const size_t n = GRID_N, st = 3 * n;
-    gridb200::Span ins[1] = {{hd->h_q_qd_u, hd->d_q_qd_u, st}};
-    return gridb200::run_pipelined(hd, T, ins, 1, {hd->h_qdd, hd->d_qdd, n},
+    GRID_NS::Span ins[1] = {{hd->h_q_qd_u, hd->d_q_qd_u, st}};
+    return GRID_NS::run_pipelined(hd, T, ins, 1, {hd->h_qdd, hd->d_qdd, n},
         [&](size_t first, int cnt, cudaStream_t s) {
             return grid_forward_dynamics_device(hd->d_qdd + first * n, hd->d_q_qd_u + first * st, (int)st, cnt,
                                                 gravity, s);
@@ -254,12 +254,12 @@ int grid_forward_dynamics(grid_data *hd, int T, float gravity) {
 }
 
 int grid_inverse_dynamics_gradient(grid_data *hd, int T, float gravity, int use_qdd, int compressed) {
-    if (!hd) return gridb200::fail_msg("null grid_data");
+    if (!hd) return GRID_NS::fail_msg("null grid_data");
     const size_t n = GRID_N, st = compressed ? 2 * n : 3 * n;
-    gridb200::Span ins[2] = {{compressed ? hd->h_q_qd : hd->h_q_qd_u, compressed ? hd->d_q_qd : hd->d_q_qd_u, st},
+    GRID_NS::Span ins[2] = {{compressed ? hd->h_q_qd : hd->h_q_qd_u, compressed ? hd->d_q_qd : hd->d_q_qd_u, st},
                              {hd->h_qdd, hd->d_qdd, n}};
     float *d_in = ins[0].d;
-    return gridb200::run_pipelined(hd, T, ins, use_qdd ? 2 : 1, {hd->h_dc_du, hd->d_dc_du, 2 * n * n},
+    return GRID_NS::run_pipelined(hd, T, ins, use_qdd ? 2 : 1, {hd->h_dc_du, hd->d_dc_du, 2 * n * n},
         [&](size_t first, int cnt, cudaStream_t s) {
             return grid_inverse_dynamics_gradient_device(hd->d_dc_du + first * 2 * n * n, d_in + first * st, (int)st,
                                                          use_qdd ? hd->d_qdd + first * n : nullptr, cnt, gravity, s);
@@ -267,10 +267,10 @@ int grid_inverse_dynamics_gradient(grid_data *hd, int T, float gravity, int use_
 }
 
 int grid_forward_dynamics_gradient(grid_data *hd, int T, float gravity, int use_qdd_minv) {
-    if (!hd) return gridb200::fail_msg("null grid_data");
+    if (!hd) return GRID_NS::fail_msg("null grid_data");
     const size_t n = GRID_N, st = 3 * n;
-    gridb200::Span ins[3] = {{hd->h_q_qd_u, hd->d_q_qd_u, st}, {hd->h_qdd, hd->d_qdd, n}, {hd->h_Minv, hd->d_Minv, n * n}};
-    return gridb200::run_pipelined(hd, T, ins, use_qdd_minv ? 3 : 1, {hd->h_df_du, hd->d_df_du, 2 * n * n},
+    GRID_NS::Span ins[3] = {{hd->h_q_qd_u, hd->d_q_qd_u, st}, {hd->h_qdd, hd->d_qdd, n}, {hd->h_Minv, hd->d_Minv, n * n}};
+    return GRID_NS::run_pipelined(hd, T, ins, use_qdd_minv ? 3 : 1, {hd->h_df_du, hd->d_df_du, 2 * n * n},
         [&](size_t first, int cnt, cudaStream_t s) {
             return grid_forward_dynamics_gradient_device(
                 hd->d_df_du + first * 2 * n * n, hd->d_q_qd_u + first * st, (int)st,
@@ -282,7 +282,7 @@ int grid_forward_dynamics_gradient(grid_data *hd, int T, float gravity, int use_
 }  // extern "C"
 
 /* ---- FP32 roofline microbenchmark ------------------------------------------------------ */
-namespace gridb200 {
+namespace GRID_NS {
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float a, float b) {
     float x[8];
 #pragma unroll
@@ -299,10 +299,10 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, f
     for (int k = 0; k < 8; k++) s += x[k];
     if (s == 123.456f) out[0] = s;
 }
-}  // namespace gridb200
+}  // namespace GRID_NS
 
 extern "C" double grid_measure_fp32_tflops(int repeats) {
-    using namespace gridb200;
+    using namespace GRID_NS;
     float *d = nullptr;
     if (cudaMalloc(&d, 4) != cudaSuccess) { fail_msg("cudaMalloc failed in grid_measure_fp32_tflops"); return -1.0; }
     cudaDeviceProp prop;

@@ -10,7 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
-namespace gridb200 {
+namespace GRID_NS {
 
 constexpr int odd_pad(int words) { return words | 1; }   // odd stride => conflict-free lane access
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
@@ -41,7 +41,10 @@ __device__ __forceinline__ void tile_load(float *sw, int word_off, const float *
     }
 }
 
-// One warp = one tile of 32 consecutive states; warps stride over tiles.
+// One warp = one tile of 32 consecutive states.  All warps of a CTA run the loop the same
+// number of times (a warp without a tile computes on stale data and stores nothing), because
+// the traced program may contain CTA-wide barriers: they keep the warps of an SM on the same
+// instruction-cache lines of the long straight-line program.
 template <class A, int WARPS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(32 * WARPS, MIN_BLOCKS)
 tps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0,
@@ -52,15 +55,16 @@ tps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int strid
     const int warp = threadIdx.x >> 5;
     float *sw = smem + warp * S::WARP_WORDS;
     const int ntiles = (num_states + 31) >> 5;
-    for (int tile = blockIdx.x * WARPS + warp; tile < ntiles; tile += gridDim.x * WARPS) {
+    for (int tile0 = blockIdx.x * WARPS; tile0 < ntiles; tile0 += gridDim.x * WARPS) {
+        const int tile = tile0 + warp;
         const long long first = (long long)tile * 32;
-        const int cnt = min(32, num_states - (int)first);
+        const int cnt = max(0, min(32, num_states - (int)first));
         tile_load<A::IN0, S::IN_PAD>(sw, 0, d_in0, first, stride0, cnt, lane);
         tile_load<A::IN1, S::IN_PAD>(sw, A::IN0, d_in1, first, A::IN1, cnt, lane);
         tile_load<A::IN2, S::IN_PAD>(sw, A::IN0 + A::IN1, d_in2, first, A::IN2, cnt, lane);
         __syncwarp();
         // lanes past the end of a ragged tile recompute the last valid state (results dropped)
-        const int src = min(lane, cnt - 1);
+        const int src = max(0, min(lane, cnt - 1));
         A::eval(sw + src * S::IN_PAD, sw + lane * S::OUT_PAD, gravity);
         __syncwarp();
         float *dst = d_out + first * A::OUT;
@@ -87,10 +91,17 @@ cudaError_t tps_launch(float *d_out, const float *d_in0, int stride0, const floa
     }
     const int ntiles = (num_states + 31) / 32;
     int blocks = (ntiles + WARPS - 1) / WARPS;
-    const int cap = 148 * 32;                   // beyond this, warps loop over tiles
+    static int cap = 0;                         // resident CTAs on this device; beyond it, CTAs loop
+    if (cap == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * WARPS, smem_bytes);
+        cap = sms * (per_sm > 0 ? per_sm : 1);
+    }
     if (blocks > cap) blocks = cap;
     kern<<<blocks, 32 * WARPS, smem_bytes, stream>>>(d_out, d_in0, stride0, d_in1, d_in2, num_states, gravity);
     return cudaGetLastError();
 }
 
-}  // namespace gridb200
+}  // namespace GRID_NS
