@@ -138,19 +138,120 @@ def emit_alg_struct(robot: Robot, variant: str, p: Optional[Program] = None,
     return "\n".join(txt), cnt
 
 
+def _alloc_f_slots(robot: Robot):
+    """Slot indices for the F columns of the Minv passes (csrc/grid_wps.cuh): a joint's F
+    lives from the step its first child writes it (backward) / it is produced (forward)
+    until its last reader is done, so only joints on the current root path hold a slot."""
+    n = robot.n
+    children = [[c for c in range(n) if robot.parent[c] == i] for i in range(n)]
+    slot_b, live, nslot = [-1] * n, set(), 0
+
+    def take():
+        nonlocal nslot
+        k = 0
+        while k in live:
+            k += 1
+        live.add(k)
+        nslot = max(nslot, k + 1)
+        return k
+
+    for i in range(n - 1, -1, -1):
+        par = robot.parent[i]
+        if par >= 0 and slot_b[par] < 0:
+            slot_b[par] = take()
+        if slot_b[i] >= 0:
+            live.discard(slot_b[i])
+    slot_f, live = [-1] * n, set()
+    for i in range(n):
+        par = robot.parent[i]
+        if children[i]:
+            slot_f[i] = take()
+        if par >= 0 and children[par][-1] == i:
+            live.discard(slot_f[par])
+    return slot_b, slot_f, max(nslot, 1)
+
+
+def wps_layout(robot: Robot) -> Dict[str, object]:
+    """Generation-time tables and sizes of the wide (CTA-per-state) kernels."""
+    n = robot.n
+    level = [robot.get_bfs_level_by_id(i) for i in range(n)]
+    nsub = [len(robot.get_subtree_by_id(i)) for i in range(n)]
+    nchild = [sum(1 for c in range(n) if robot.parent[c] == i) for i in range(n)]
+    slot_b, slot_f, nslot = _alloc_f_slots(robot)
+    save = [-1] * n
+    for i in range(n):
+        if nchild[i] >= 2:
+            save[i] = sum(1 for a in robot.get_ancestors_by_id(i) if nchild[a] >= 2)
+    nsave = max([x + 1 for x in save] + [1])
+    dfbase, acc = [], 0
+    for i in range(n):
+        dfbase.append(acc)
+        acc += 6 * (level[i] + 1)
+    df_words = acc
+    minv_col_warps = (n + 31) // 32
+    col_warps = (2 * n + 31) // 32
+    nt = 32 * max(col_warps, minv_col_warps + 2)
+    # mirror of struct L in csrc/grid_wps.cuh
+    Er = (5 * n + 3) // 4 * 4
+    IA = Er + 12 * n + 30 * n + n * n
+    minv_end = IA + 36 * n + 13 * n + nslot * 6 * n
+    grad_end = IA + 2 * df_words + nsave * 24 * n + 2 * n * n
+    total = (max(minv_end, grad_end) + 3) // 4 * 4
+    return dict(N=n, NT=nt, NSLOT=nslot, NSAVE=nsave, DF_WORDS=df_words, IA_LANE0=32 * minv_col_warps,
+                RNEA_TID=nt - 32, COL_WARPS=col_warps, level=level, nsub=nsub, slot_b=slot_b, slot_f=slot_f,
+                save=save, dfbase=dfbase, smem_bytes=4 * total)
+
+
+def emit_wps_tables(robot: Robot, lay: Dict[str, object]) -> str:
+    n = robot.n
+
+    def ints(name, vals):
+        return "__constant__ int %s[%d] = {%s};\n" % (name, len(vals), ", ".join(str(int(v)) for v in vals))
+
+    def floats(name, vals):
+        return "__constant__ float %s[%d] = {%s};\n" % (name, len(vals), ", ".join(_flit(float(v)) for v in vals))
+
+    t = ["namespace GRID_NS { namespace gen {\n", "struct WT {\n"]
+    for k in ("N", "NT", "NSLOT", "NSAVE", "DF_WORDS", "IA_LANE0", "RNEA_TID", "COL_WARPS"):
+        t.append("    static constexpr int %s = %d;\n" % (k, lay[k]))
+    t.append("};\n")
+    t.append(ints("wt_parent", robot.parent))
+    t.append(ints("wt_S", robot.S_ind))
+    t.append(ints("wt_nsub", lay["nsub"]))
+    t.append(ints("wt_level", lay["level"]))
+    t.append(ints("wt_fslot_b", lay["slot_b"]))
+    t.append(ints("wt_fslot_f", lay["slot_f"]))
+    t.append(ints("wt_saveslot", lay["save"]))
+    t.append(ints("wt_dfbase", lay["dfbase"]))
+    t.append(floats("wt_E0", [x for i in range(n) for x in robot.E0[i].flatten()]))
+    t.append(floats("wt_r0", [x for i in range(n) for x in robot.r0[i]]))
+    t.append(floats("wt_I", [x for i in range(n) for x in robot.Imats[i].flatten()]))
+    t.append(floats("wt_damping", robot.damping))
+    t.append("}}  // namespace GRID_NS::gen\n")
+    t.append('#include "grid_wps.cuh"\n')
+    return "".join(t)
+
+
 class KernelPlan:
     """Which kernel family serves each algorithm of a robot, and its launch shape."""
 
     def __init__(self, robot: Robot, tps_max_flops: int = 60000, tps_warps: int = 1,
-                 tps_min_blocks: Optional[Dict[str, int]] = None, tps_sync_every: int = 0):
+                 tps_min_blocks: Optional[Dict[str, int]] = None, tps_sync_every: int = 0,
+                 wps_max_states: int = 1024):
         self.robot = robot
         self.tps_warps = tps_warps
         self.tps_sync_every = tps_sync_every if tps_warps > 1 else 0
         alg = algorithmic_flops(robot)
         self.kind: Dict[str, str] = {}
+        self.wps = wps_layout(robot)
+        self.wps_ok = self.wps["smem_bytes"] <= 227 * 1024
+        # batches up to this many states go to the wide kernel when both exist (latency mode)
+        self.wps_max_states = wps_max_states
         for a in ("id", "minv", "fd", "id_grad", "fd_grad"):
             # the dense reference count over-states traced work by ~4x; gate on it
-            self.kind[a] = "tps" if alg[a] <= tps_max_flops else "none"
+            tps = alg[a] <= tps_max_flops
+            wps = self.wps_ok and a != "id"
+            self.kind[a] = "tps+wps" if tps and wps else "tps" if tps else "wps" if wps else "none"
         # resident single-warp CTAs per SM = register cap 65536/(32*min_blocks).  Measured on B200
         # (profiles/r1_sweep_tps.md): the gradient programs spill at 128/168 registers and run
         # 2.1x faster at 255 registers with no spills; the small programs fit 128.
@@ -195,7 +296,7 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
     needed = {"id": ("id", "id_qdd"), "minv": ("minv",), "fd": ("fd",), "id_grad": ("id_grad", "id_grad_qdd"),
               "fd_grad": ("fd_grad", "fd_grad_qdd_minv")}
     for a, variants in needed.items():
-        if plan.kind[a] != "tps":
+        if "tps" not in plan.kind[a]:
             continue
         for v in variants:
             txt, cnt = emit_alg_struct(robot, v, sync_every=plan.tps_sync_every)
@@ -204,51 +305,72 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
     out.append("}}  // namespace GRID_NS::gen\n")
 
     W = plan.tps_warps
+    has_tps = lambda a: "tps" in plan.kind[a]
+    has_wps = lambda a: "wps" in plan.kind[a]
+    if any(has_wps(a) for a in plan.kind):
+        out.append(emit_wps_tables(robot, plan.wps))
 
     def tps(a, struct):
         return "tps_launch<%s, %d, %d>" % (struct, W, plan.min_blocks[a])
 
+    def body(a, tps_call, wps_call):
+        """tps_call / wps_call: list of (condition or None, expression)."""
+        lines = []
+        if has_tps(a) and has_wps(a):
+            lines.append("    if (use_wide(N)) {")
+            lines += ["        %sreturn %s;" % ("if (%s) " % c if c else "", e) for c, e in wps_call]
+            lines.append("    }")
+            lines += ["    %sreturn %s;" % ("if (%s) " % c if c else "", e) for c, e in tps_call]
+        elif has_tps(a):
+            lines += ["    %sreturn %s;" % ("if (%s) " % c if c else "", e) for c, e in tps_call]
+        elif has_wps(a):
+            lines += ["    %sreturn %s;" % ("if (%s) " % c if c else "", e) for c, e in wps_call]
+        else:
+            lines.append("    return cudaErrorNotSupported;")
+        return lines
+
     L: List[str] = []
-    unsupported = "    return cudaErrorNotSupported;"
+    L.append("// batches up to WPS_MAX_STATES use the wide kernels when both families exist; the\n"
+             "// environment variable GRID_FORCE_KERNEL=tps|wps overrides (tests exercise both).\n"
+             "static bool use_wide(int N) {\n"
+             "    const char *f = getenv(\"GRID_FORCE_KERNEL\");\n"
+             "    if (f && !strcmp(f, \"wps\")) return true;\n"
+             "    if (f && !strcmp(f, \"tps\")) return false;\n"
+             "    return N <= %d;\n}" % plan.wps_max_states)
     L.append("cudaError_t launch_id(float *d_c, const float *d_q_qd, int stride, const float *d_qdd, int N, float g,"
              " cudaStream_t s) {")
-    if plan.kind["id"] == "tps":
-        L.append("    if (d_qdd) return %s(d_c, d_q_qd, stride, d_qdd, nullptr, N, g, s);" % tps("id", "AlgIdQdd"))
-        L.append("    return %s(d_c, d_q_qd, stride, nullptr, nullptr, N, g, s);" % tps("id", "AlgId"))
-    else:
-        L.append(unsupported)
+    L += body("id", [("d_qdd", "%s(d_c, d_q_qd, stride, d_qdd, nullptr, N, g, s)" % tps("id", "AlgIdQdd")),
+                     (None, "%s(d_c, d_q_qd, stride, nullptr, nullptr, N, g, s)" % tps("id", "AlgId"))], [])
     L.append("}")
     L.append("cudaError_t launch_minv(float *d_Minv, const float *d_q, int stride, int N, cudaStream_t s) {")
-    L.append("    return %s(d_Minv, d_q, stride, nullptr, nullptr, N, 0.f, s);" % tps("minv", "AlgMinv")
-             if plan.kind["minv"] == "tps" else unsupported)
+    L += body("minv", [(None, "%s(d_Minv, d_q, stride, nullptr, nullptr, N, 0.f, s)" % tps("minv", "AlgMinv"))],
+              [(None, "wps::wps_launch<0, false>(d_Minv, d_q, stride, nullptr, nullptr, N, 0.f, s)")])
     L.append("}")
     L.append("cudaError_t launch_fd(float *d_qdd, const float *d_q_qd_u, int stride, int N, float g, cudaStream_t s) {")
-    L.append("    return %s(d_qdd, d_q_qd_u, stride, nullptr, nullptr, N, g, s);" % tps("fd", "AlgFd")
-             if plan.kind["fd"] == "tps" else unsupported)
+    L += body("fd", [(None, "%s(d_qdd, d_q_qd_u, stride, nullptr, nullptr, N, g, s)" % tps("fd", "AlgFd"))],
+              [(None, "wps::wps_launch<1, false>(d_qdd, d_q_qd_u, stride, nullptr, nullptr, N, g, s)")])
     L.append("}")
     L.append("cudaError_t launch_id_grad(float *d_dc_du, const float *d_q_qd, int stride, const float *d_qdd, int N,"
              " float g, cudaStream_t s) {")
-    if plan.kind["id_grad"] == "tps":
-        L.append("    if (d_qdd) return %s(d_dc_du, d_q_qd, stride, d_qdd, nullptr, N, g, s);"
-                 % tps("id_grad", "AlgIdGradQdd"))
-        L.append("    return %s(d_dc_du, d_q_qd, stride, nullptr, nullptr, N, g, s);" % tps("id_grad", "AlgIdGrad"))
-    else:
-        L.append(unsupported)
+    L += body("id_grad",
+              [("d_qdd", "%s(d_dc_du, d_q_qd, stride, d_qdd, nullptr, N, g, s)" % tps("id_grad", "AlgIdGradQdd")),
+               (None, "%s(d_dc_du, d_q_qd, stride, nullptr, nullptr, N, g, s)" % tps("id_grad", "AlgIdGrad"))],
+              [("d_qdd", "wps::wps_launch<2, true>(d_dc_du, d_q_qd, stride, d_qdd, nullptr, N, g, s)"),
+               (None, "wps::wps_launch<2, false>(d_dc_du, d_q_qd, stride, nullptr, nullptr, N, g, s)")])
     L.append("}")
     L.append("cudaError_t launch_fd_grad(float *d_df_du, const float *d_in, int stride, const float *d_qdd,"
              " const float *d_Minv, int N, float g, cudaStream_t s) {")
-    if plan.kind["fd_grad"] == "tps":
-        L.append("    if (d_qdd) return %s(d_df_du, d_in, stride, d_qdd, d_Minv, N, g, s);"
-                 % tps("fd_grad", "AlgFdGradPre"))
-        L.append("    return %s(d_df_du, d_in, stride, nullptr, nullptr, N, g, s);" % tps("fd_grad", "AlgFdGrad"))
-    else:
-        L.append(unsupported)
+    L += body("fd_grad",
+              [("d_qdd", "%s(d_df_du, d_in, stride, d_qdd, d_Minv, N, g, s)" % tps("fd_grad", "AlgFdGradPre")),
+               (None, "%s(d_df_du, d_in, stride, nullptr, nullptr, N, g, s)" % tps("fd_grad", "AlgFdGrad"))],
+              [("d_qdd", "wps::wps_launch<3, true>(d_df_du, d_in, stride, d_qdd, d_Minv, N, g, s)"),
+               (None, "wps::wps_launch<3, false>(d_df_du, d_in, stride, nullptr, nullptr, N, g, s)")])
     L.append("}")
 
     kinds = "\n".join('    if (!strcmp(alg, "%s")) return "%s";' % (a, k) for a, k in plan.kind.items())
     fl = "\n".join('    if (!strcmp(alg, "%s")) return %d;' % (a, stats[needed[a][0]]["flops"])
-                   for a in plan.kind if plan.kind[a] == "tps")
-    out.append("#include <cstring>\n")
+                   for a in plan.kind if "tps" in plan.kind[a])
+    out.append("#include <cstring>\n#include <cstdlib>\n")
     out.append(_LAUNCHERS % {"launchers": "\n".join(L), "kinds": kinds, "flops": fl})
     out.append('#include "grid_abi.cuh"\n')
     return "".join(out), stats

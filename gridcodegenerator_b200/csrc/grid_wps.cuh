@@ -1,0 +1,579 @@
+// grid_wps.cuh - "wide" kernels: one CTA per state, lanes = columns.
+//
+// Used where one thread per state is not viable: robots whose traced program is too
+// large (Atlas, chain-64: Minv / FD / ID-gradient / FD-gradient) and, for small robots,
+// small batches where latency matters (N = 128 knot points).  Replaces the reference's
+// block-per-state kernels (algorithms/_direct_minv.py:23-382,
+// _inverse_dynamics_gradient.py:27-650, _forward_dynamics_gradient.py:7-57) with a
+// different decomposition:
+//   * every du-column (dq_j or dqd_j) of the gradient and every column of Minv/F is owned
+//     by ONE lane for the whole recursion, so there are no shared-memory atomics and no
+//     barrier inside a gradient pass (the reference has 26-197); the Minv
+//     passes need one named barrier per joint;
+//   * the two RNEA sweeps run on their own warp, concurrently with the Minv passes;
+//   * X_i is kept as (E, r) (12 floats) and applied as two 3x3 products and a cross
+//     product (27 FMA) instead of a dense 6x6 (36);
+//   * F and the per-column df storage are slot-allocated at generation time from the tree
+//     (F: live ancestors only; df: 6*(|anc|+1) per joint), which is what makes the 64-link
+//     chain fit: the reference needs 431-519 KB of shared memory per block for its
+//     gradients, this layout needs ~160 KB.
+// The generated translation unit provides, in GRID_NS::gen, `struct WT` (sizes) and the
+// __constant__ tables wt_* before including this file.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace GRID_NS { namespace wps {
+
+using namespace gen;
+constexpr int N = WT::N;
+constexpr int NT = WT::NT;
+
+// ---- shared memory layout (floats) ----------------------------------------------------
+struct L {
+    static constexpr int q = 0, qd = q + N, u = qd + N, qdd = u + N, c = qdd + N;
+    static constexpr int Er = ((c + N + 3) / 4) * 4;          // 12 per joint, float4 aligned
+    static constexpr int v = Er + 12 * N, a = v + 6 * N, f = a + 6 * N, Xa = f + 6 * N, Iv = Xa + 6 * N;
+    static constexpr int Minv = Iv + 6 * N;                    // N*N row-major [row][col], upper
+    static constexpr int IA = Minv + N * N;                    // 36 per joint, row-major
+    static constexpr int U = IA + 36 * N, W = U + 6 * N, Dinv = W + 6 * N;
+    static constexpr int F = Dinv + N;                         // NSLOT * 6 * N, [slot][row][col]
+    static constexpr int minv_end = F + WT::NSLOT * 6 * N;
+    // the gradient region aliases the Minv scratch (IA, U, W, Dinv, F are dead by then)
+    static constexpr int df = IA;                              // 2 * DF_WORDS
+    static constexpr int sv = df + 2 * WT::DF_WORDS;           // NSAVE * 12 * 2N  [slot][12][col]
+    static constexpr int dc = sv + WT::NSAVE * 12 * 2 * N;     // 2N * N  [col][row] == output layout
+    static constexpr int grad_end = dc + 2 * N * N;
+    static constexpr int total = ((minv_end > grad_end ? minv_end : grad_end) + 3) / 4 * 4;
+};
+
+// ---- per-thread spatial algebra ---------------------------------------------------------
+struct Xf { float E[9]; float r[3]; };
+
+__device__ __forceinline__ Xf load_X(const float *s, int i) {
+    Xf x;
+    const float4 *p = reinterpret_cast<const float4 *>(s + L::Er + 12 * i);
+    float4 a = p[0], b = p[1], c = p[2];
+    x.E[0] = a.x; x.E[1] = a.y; x.E[2] = a.z; x.E[3] = a.w; x.E[4] = b.x; x.E[5] = b.y; x.E[6] = b.z; x.E[7] = b.w;
+    x.E[8] = c.x; x.r[0] = c.y; x.r[1] = c.z; x.r[2] = c.w;
+    return x;
+}
+__device__ __forceinline__ void load6(const float *p, float *o) {
+#pragma unroll
+    for (int r = 0; r < 6; r++) o[r] = p[r];
+}
+__device__ __forceinline__ void store6(float *p, const float *o) {
+#pragma unroll
+    for (int r = 0; r < 6; r++) p[r] = o[r];
+}
+__device__ __forceinline__ void cross3(const float *a, const float *b, float *o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ void mat3(const float *E, const float *x, float *o) {
+    o[0] = E[0] * x[0] + E[1] * x[1] + E[2] * x[2];
+    o[1] = E[3] * x[0] + E[4] * x[1] + E[5] * x[2];
+    o[2] = E[6] * x[0] + E[7] * x[1] + E[8] * x[2];
+}
+__device__ __forceinline__ void mat3T(const float *E, const float *x, float *o) {
+    o[0] = E[0] * x[0] + E[3] * x[1] + E[6] * x[2];
+    o[1] = E[1] * x[0] + E[4] * x[1] + E[7] * x[2];
+    o[2] = E[2] * x[0] + E[5] * x[1] + E[8] * x[2];
+}
+// X v (motion vector): [E w ; E (l - r x w)]
+__device__ __forceinline__ void xmotion(const Xf &X, const float *v, float *o) {
+    float t[3];
+    cross3(X.r, v, t);
+    t[0] = v[3] - t[0]; t[1] = v[4] - t[1]; t[2] = v[5] - t[2];
+    mat3(X.E, v, o);
+    mat3(X.E, t, o + 3);
+}
+// X^T f (force vector): [E^T n + r x (E^T fl) ; E^T fl]
+__device__ __forceinline__ void xtforce(const Xf &X, const float *f, float *o) {
+    float t[3];
+    mat3T(X.E, f + 3, o + 3);
+    mat3T(X.E, f, o);
+    cross3(X.r, o + 3, t);
+    o[0] += t[0]; o[1] += t[1]; o[2] += t[2];
+}
+// w x e_a  (a is warp-uniform)
+__device__ __forceinline__ void wxe(int a, const float *w, float *o) {
+    switch (a) {
+        case 0: o[0] = 0.f; o[1] = w[2]; o[2] = -w[1]; break;
+        case 1: o[0] = -w[2]; o[1] = 0.f; o[2] = w[0]; break;
+        default: o[0] = w[1]; o[1] = -w[0]; o[2] = 0.f; break;
+    }
+}
+// (v x) e_k : the reference's mx0..mx5 (helpers/_spatial_algebra_helpers.py:62-147)
+__device__ __forceinline__ void mxS(int k, const float *v, float *o) {
+    if (k < 3) {
+        wxe(k, v, o);
+        wxe(k, v + 3, o + 3);
+    } else {
+        o[0] = o[1] = o[2] = 0.f;
+        wxe(k - 3, v, o + 3);
+    }
+}
+__device__ __forceinline__ float pick(const float *v, int k) {
+    switch (k) {
+        case 0: return v[0];
+        case 1: return v[1];
+        case 2: return v[2];
+        case 3: return v[3];
+        case 4: return v[4];
+        default: return v[5];
+    }
+}
+__device__ __forceinline__ void add_at(float *v, int k, float x) {
+    switch (k) {
+        case 0: v[0] += x; break;
+        case 1: v[1] += x; break;
+        case 2: v[2] += x; break;
+        case 3: v[3] += x; break;
+        case 4: v[4] += x; break;
+        default: v[5] += x; break;
+    }
+}
+// v x* f : fx_times_v (helpers/_spatial_algebra_helpers.py:181-256)
+__device__ __forceinline__ void crossf(const float *v, const float *f, float *o) {
+    float t[3];
+    cross3(v, f, o);
+    cross3(v + 3, f + 3, t);
+    o[0] += t[0]; o[1] += t[1]; o[2] += t[2];
+    cross3(v, f + 3, o + 3);
+}
+// I_i v with the inertia in constant memory (i is warp-uniform)
+__device__ __forceinline__ void imul(int i, const float *v, float *o) {
+    const float *I = wt_I + 36 * i;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 6; c++) acc = fmaf(I[6 * r + c], v[c], acc);
+        o[r] = acc;
+    }
+}
+
+// ---- X(q): E = E_joint(q) E0, r = r0 (+ q * E0[k-3,:] for prismatic) ---------------------
+// replaces load_update_XImats_helpers (helpers/_topology_helpers.py:90-182)
+__device__ __forceinline__ void update_X(float *s, int i) {
+    const int k = wt_S[i];
+    const float *E0 = wt_E0 + 9 * i;
+    float E[9], r[3] = {wt_r0[3 * i], wt_r0[3 * i + 1], wt_r0[3 * i + 2]};
+#pragma unroll
+    for (int e = 0; e < 9; e++) E[e] = E0[e];
+    const float qi = s[L::q + i];
+    if (k < 3) {
+        float sn, cs;
+        sincosf(qi, &sn, &cs);
+        const int a = (k + 1) % 3, b = (k + 2) % 3;
+#pragma unroll
+        for (int col = 0; col < 3; col++) {
+            const float ea = E0[3 * a + col], eb = E0[3 * b + col];
+            const float na = cs * ea + sn * eb, nb = cs * eb - sn * ea;
+            // rows a and b are warp-divergent indices only across joints; write through selects
+#pragma unroll
+            for (int row = 0; row < 3; row++) {
+                if (row == a) E[3 * row + col] = na;
+                if (row == b) E[3 * row + col] = nb;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 3; t++) r[t] += qi * E0[3 * (k - 3) + t];
+    }
+    float *dst = s + L::Er + 12 * i;
+#pragma unroll
+    for (int e = 0; e < 9; e++) dst[e] = E[e];
+    dst[9] = r[0]; dst[10] = r[1]; dst[11] = r[2];
+}
+
+// ---- RNEA, one thread, joints in id order (parent < child) --------------------------------
+// replaces inverse_dynamics_inner / _vaf (algorithms/_inverse_dynamics.py:33-304)
+__device__ void rnea_serial(float *s, bool use_qdd, float gravity) {
+    for (int i = 0; i < N; i++) {
+        const Xf X = load_X(s, i);
+        const int par = wt_parent[i], k = wt_S[i];
+        float v[6], a[6], xa[6], t[6], iv[6], f[6];
+        if (par < 0) {
+            const float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, gravity};
+#pragma unroll
+            for (int r = 0; r < 6; r++) v[r] = 0.f;
+            xmotion(X, g, xa);
+        } else {
+            float vp[6], ap[6];
+            load6(s + L::v + 6 * par, vp);
+            load6(s + L::a + 6 * par, ap);
+            xmotion(X, vp, v);
+            xmotion(X, ap, xa);
+        }
+        const float qdi = s[L::qd + i];
+        add_at(v, k, qdi);
+#pragma unroll
+        for (int r = 0; r < 6; r++) a[r] = xa[r];
+        if (use_qdd) add_at(a, k, s[L::qdd + i]);
+        if (par >= 0) {
+            mxS(k, v, t);
+#pragma unroll
+            for (int r = 0; r < 6; r++) a[r] = fmaf(t[r], qdi, a[r]);
+        }
+        imul(i, v, iv);
+        imul(i, a, f);
+        crossf(v, iv, t);
+#pragma unroll
+        for (int r = 0; r < 6; r++) f[r] += t[r];
+        store6(s + L::v + 6 * i, v);
+        store6(s + L::a + 6 * i, a);
+        store6(s + L::Xa + 6 * i, xa);
+        store6(s + L::Iv + 6 * i, iv);
+        store6(s + L::f + 6 * i, f);
+    }
+    for (int i = N - 1; i >= 0; i--) {
+        const int par = wt_parent[i], k = wt_S[i];
+        float f[6];
+        load6(s + L::f + 6 * i, f);
+        s[L::c + i] = pick(f, k) + wt_damping[i] * s[L::qd + i];
+        if (par >= 0) {
+            const Xf X = load_X(s, i);
+            float t[6];
+            xtforce(X, f, t);
+#pragma unroll
+            for (int r = 0; r < 6; r++) s[L::f + 6 * par + r] += t[r];
+        }
+    }
+}
+
+// barrier among the threads that run the Minv passes (every warp except the RNEA warp)
+__device__ __forceinline__ void minv_bar() {
+    asm volatile("bar.sync 1, %0;" ::"n"(NT - 32) : "memory");
+}
+
+// ---- Minv: both passes.  Called by all threads with tid < NT-32 ------------------------------
+// replaces direct_minv_inner (algorithms/_direct_minv.py:23-382; oracle _test.py:117-226)
+__device__ void minv_passes(float *s, int tid) {
+    // backward pass, children before parents
+    for (int i = N - 1; i >= 0; i--) {
+        const int par = wt_parent[i], k = wt_S[i], nsub = wt_nsub[i];
+        const Xf X = load_X(s, i);
+        const float *IAi = s + L::IA + 36 * i;
+        float U[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) U[r] = IAi[6 * r + k];
+        const float Dinv = 1.0f / pick(U, k);
+        for (int t = tid; t < nsub; t += NT - 32) {
+            const int j = i + t;
+            float Fij[6];
+            const float *Fs = s + L::F + wt_fslot_b[i] * 6 * N + j;
+#pragma unroll
+            for (int r = 0; r < 6; r++) Fij[r] = (t == 0) ? 0.f : Fs[r * N];
+            const float m = (t == 0 ? Dinv : 0.f) - Dinv * pick(Fij, k);
+            s[L::Minv + i * N + j] = m;
+            if (par >= 0) {
+                float o[6];
+#pragma unroll
+                for (int r = 0; r < 6; r++) Fij[r] = fmaf(U[r], m, Fij[r]);
+                xtforce(X, Fij, o);
+                float *Fp = s + L::F + wt_fslot_b[par] * 6 * N + j;
+#pragma unroll
+                for (int r = 0; r < 6; r++) Fp[r * N] = o[r];
+            }
+            if (t == 0) {
+                float w[6];
+                xtforce(X, U, w);
+                s[L::Dinv + i] = Dinv;
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    s[L::U + 6 * i + r] = U[r];
+                    s[L::W + 6 * i + r] = w[r] * Dinv;
+                }
+            }
+        }
+        // articulated inertia: IA[par] += X^T (IA - U Dinv U^T) X, one lane per column
+        const int cl = tid - WT::IA_LANE0;
+        if (par >= 0 && cl >= 0 && cl < 6) {
+            float e[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, x[6], t[6], o[6];
+            add_at(e, cl, 1.0f);
+            xmotion(X, e, x);
+            float ux = 0.f;
+#pragma unroll
+            for (int r = 0; r < 6; r++) ux = fmaf(U[r], x[r], ux);
+            ux *= Dinv;
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                float acc = -U[r] * ux;
+#pragma unroll
+                for (int c = 0; c < 6; c++) acc = fmaf(IAi[6 * r + c], x[c], acc);
+                t[r] = acc;
+            }
+            xtforce(X, t, o);
+            float *IAp = s + L::IA + 36 * par;
+#pragma unroll
+            for (int r = 0; r < 6; r++) IAp[6 * r + cl] += o[r];
+        }
+        minv_bar();
+    }
+    // forward pass, serial over joints ("CANNOT BE IN PARALLEL BY BFS_LEVEL", _test.py:191)
+    for (int i = 0; i < N; i++) {
+        const int par = wt_parent[i], k = wt_S[i];
+        const Xf X = load_X(s, i);
+        float w[6];
+        load6(s + L::W + 6 * i, w);
+        for (int t = tid; t < N - i; t += NT - 32) {
+            const int j = i + t;
+            float m = s[L::Minv + i * N + j];
+            float Fp[6], Fij[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (par >= 0) {
+                const float *Fs = s + L::F + wt_fslot_f[par] * 6 * N + j;
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    Fp[r] = Fs[r * N];
+                    m = fmaf(-w[r], Fp[r], m);
+                }
+                s[L::Minv + i * N + j] = m;
+            }
+            if (wt_fslot_f[i] >= 0) {
+                if (par >= 0) xmotion(X, Fp, Fij);
+                add_at(Fij, k, m);
+                float *Fd = s + L::F + wt_fslot_f[i] * 6 * N + j;
+#pragma unroll
+                for (int r = 0; r < 6; r++) Fd[r * N] = Fij[r];
+            }
+        }
+        minv_bar();
+    }
+}
+
+__device__ __forceinline__ float minv_sym(const float *s, int r, int c) {
+    return r <= c ? s[L::Minv + r * N + c] : s[L::Minv + c * N + r];
+}
+
+// ---- ID gradient: one lane per du-column, no barriers inside ---------------------------------
+// replaces inverse_dynamics_gradient_inner (algorithms/_inverse_dynamics_gradient.py:27-650;
+// oracle _test.py:229-488).  col < N: d/dq_col ; col >= N: d/dqd_(col-N).
+__device__ void grad_column(float *s, int col, bool valid) {
+    // lanes without a column (valid == false) only take part in the warp votes
+    const int sd = col >= N ? 1 : 0;
+    const int j = valid ? col - sd * N : N;
+    const int jend = valid ? j + wt_nsub[j] : j;
+    const int lj = valid ? wt_level[j] : 0;
+    float *dfp = s + L::df + sd * WT::DF_WORDS;
+    float dv[6], da[6];
+    // forward: joints of subtree(j) in id order, all lanes of the warp on the same joint
+    for (int i = 0; i < N; i++) {
+        const bool active = (i >= j) && (i < jend);
+        if (!__any_sync(0xffffffffu, active)) continue;
+        if (!active) continue;
+        const Xf X = load_X(s, i);
+        const int k = wt_S[i], par = wt_parent[i];
+        const float qdi = s[L::qd + i];
+        float vi[6], t[6];
+        load6(s + L::v + 6 * i, vi);
+        if (i == j) {
+            if (sd == 0) {
+                float xa[6];
+                load6(s + L::Xa + 6 * i, xa);
+                mxS(k, vi, dv);                       // == mxS(X v_parent)
+                mxS(k, dv, da);
+                mxS(k, xa, t);
+#pragma unroll
+                for (int r = 0; r < 6; r++) da[r] = fmaf(da[r], qdi, t[r]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 6; r++) dv[r] = 0.f;
+                add_at(dv, k, 1.0f);
+                mxS(k, vi, da);
+            }
+        } else {
+            if (par != i - 1) {                       // first joint of a later branch: reload the parent's dv, da
+                const float *p = s + L::sv + (wt_saveslot[par] * 12) * (2 * N) + col;
+#pragma unroll
+                for (int r = 0; r < 6; r++) { dv[r] = p[r * 2 * N]; da[r] = p[(6 + r) * 2 * N]; }
+            }
+            float dvn[6], dan[6];
+            xmotion(X, dv, dvn);
+            xmotion(X, da, dan);
+            mxS(k, dvn, t);
+#pragma unroll
+            for (int r = 0; r < 6; r++) { dv[r] = dvn[r]; da[r] = fmaf(t[r], qdi, dan[r]); }
+        }
+        if (wt_saveslot[i] >= 0) {
+            float *p = s + L::sv + (wt_saveslot[i] * 12) * (2 * N) + col;
+#pragma unroll
+            for (int r = 0; r < 6; r++) { p[r * 2 * N] = dv[r]; p[(6 + r) * 2 * N] = da[r]; }
+        }
+        // df = I da + dv x* (I v) + v x* (I dv)
+        float ivv[6], df[6], idv[6];
+        load6(s + L::Iv + 6 * i, ivv);
+        imul(i, da, df);
+        imul(i, dv, idv);
+        crossf(dv, ivv, t);
+#pragma unroll
+        for (int r = 0; r < 6; r++) df[r] += t[r];
+        crossf(vi, idv, t);
+        const int w = wt_level[i] + 1;
+        float *d = dfp + wt_dfbase[i] + lj;
+#pragma unroll
+        for (int r = 0; r < 6; r++) d[r * w] = df[r] + t[r];
+    }
+    // backward: subtree accumulation (i > j), leave the subtree at i == j, then up the ancestors
+    float up[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = N - 1; i >= 0; i--) {
+        const bool in_sub = (i >= j) && (i < jend);
+        const bool is_anc = valid && (i < j) && (j < i + wt_nsub[i]);
+        const bool active = in_sub || is_anc;
+        if (!__any_sync(0xffffffffu, active)) continue;
+        if (!active) continue;
+        const int k = wt_S[i], par = wt_parent[i];
+        float vec[6];
+        if (in_sub) {
+            const int w = wt_level[i] + 1;
+            const float *d = dfp + wt_dfbase[i] + lj;
+#pragma unroll
+            for (int r = 0; r < 6; r++) vec[r] = d[r * w];
+        } else {
+#pragma unroll
+            for (int r = 0; r < 6; r++) vec[r] = up[r];
+        }
+        float dcv = pick(vec, k);
+        if (sd == 1 && i == j) dcv += wt_damping[i];
+        s[L::dc + col * N + i] = dcv;
+        if (par >= 0) {
+            if (i == j && sd == 0) {
+                float fi[6], t[6];
+                load6(s + L::f + 6 * i, fi);
+                mxS(k, fi, t);
+#pragma unroll
+                for (int r = 0; r < 6; r++) vec[r] -= t[r];
+            }
+            const Xf X = load_X(s, i);
+            float o[6];
+            xtforce(X, vec, o);
+            if (i > j) {
+                const int wp = wt_level[par] + 1;
+                float *d = dfp + wt_dfbase[par] + lj;
+#pragma unroll
+                for (int r = 0; r < 6; r++) d[r * wp] += o[r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < 6; r++) up[r] = o[r];
+            }
+        }
+    }
+}
+
+// ALG: 0 = Minv, 1 = FD, 2 = ID gradient, 3 = FD gradient.
+// EXTRA: ALG 2 -> qdd given (USE_QDD_FLAG); ALG 3 -> qdd and Minv given (USE_QDD_MINV_FLAG).
+template <int ALG, bool EXTRA>
+__global__ void __launch_bounds__(NT)
+wps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in, int stride, const float *__restrict__ d_qdd,
+           const float *__restrict__ d_Minv, int num_states, float gravity) {
+    extern __shared__ float4 smem4[];
+    float *s = reinterpret_cast<float *>(smem4);
+    const int tid = threadIdx.x;
+    constexpr bool need_minv = (ALG == 0) || (ALG == 1) || (ALG == 3 && !EXTRA);
+    constexpr bool need_c0 = (ALG == 1) || (ALG == 3 && !EXTRA);
+    constexpr int n_in = (ALG == 0) ? N : ((ALG == 1 || (ALG == 3 && !EXTRA)) ? 3 * N : 2 * N);
+    constexpr int RW = WT::RNEA_TID;                 // first thread of the RNEA warp
+
+    for (long long st = blockIdx.x; st < num_states; st += gridDim.x) {
+        for (int e = tid; e < n_in; e += NT) s[L::q + e] = __ldg(d_in + st * stride + e);
+        if (EXTRA) {
+            for (int e = tid; e < N; e += NT) s[L::qdd + e] = __ldg(d_qdd + st * N + e);
+            if (ALG == 3)
+                for (int e = tid; e < N * N; e += NT) {
+                    const int cc = e / N, rr = e - cc * N;      // global is column-major, upper triangle
+                    if (rr <= cc) s[L::Minv + rr * N + cc] = __ldg(d_Minv + st * N * N + e);
+                }
+        }
+        __syncthreads();
+        for (int i = tid; i < N; i += NT) update_X(s, i);
+        if (need_minv) {
+            for (int e = tid; e < 36 * N; e += NT) s[L::IA + e] = wt_I[e];
+            for (int e = tid; e < N * N; e += NT) s[L::Minv + e] = 0.f;
+        }
+        __syncthreads();
+        // Minv passes on warps [0, RW/32), bias forces (RNEA with qdd = 0) concurrently on the RNEA warp
+        if (tid < RW) {
+            if (need_minv) minv_passes(s, tid);
+        } else if (tid == RW) {
+            if (need_c0) rnea_serial(s, false, gravity);
+        }
+        __syncthreads();
+        if (ALG == 0) {
+            float *o = d_out + st * N * N;
+            for (int e = tid; e < N * N; e += NT) {
+                const int cc = e / N, rr = e - cc * N;
+                o[e] = rr <= cc ? s[L::Minv + rr * N + cc] : 0.f;
+            }
+        }
+        if (need_c0) {        // forward_dynamics_finish (algorithms/_forward_dynamics.py:21-49)
+            for (int r = tid; r < N; r += NT) {
+                float acc = 0.f;
+                for (int k = 0; k < N; k++) acc = fmaf(minv_sym(s, r, k), s[L::u + k] - s[L::c + k], acc);
+                s[L::qdd + r] = acc;
+            }
+            __syncthreads();
+            if (ALG == 1)
+                for (int r = tid; r < N; r += NT) d_out[st * N + r] = s[L::qdd + r];
+        }
+        if (ALG >= 2) {
+            if (tid == RW) rnea_serial(s, ALG == 3 ? true : EXTRA, gravity);
+            else
+                for (int e = (tid > RW ? tid - 1 : tid); e < 2 * N * N; e += NT - 1) s[L::dc + e] = 0.f;
+            __syncthreads();
+            if (tid < WT::COL_WARPS * 32)            // whole warps: grad_column votes with a full mask
+                grad_column(s, tid < 2 * N ? tid : 2 * N - 1, tid < 2 * N);
+            __syncthreads();
+            float *o = d_out + st * 2 * N * N;
+            if (ALG == 2) {
+                for (int e = tid; e < 2 * N * N; e += NT) o[e] = s[L::dc + e];
+            } else {
+                // df_du[:, col] = -Minv dc_du[:, col]  (algorithms/_forward_dynamics_gradient.py:48-57)
+                // each lane owns one column: read it into registers, overwrite it in place
+                for (int col = tid; col < 2 * N; col += NT) {
+                    float dcol[N];
+#pragma unroll
+                    for (int k = 0; k < N; k++) dcol[k] = s[L::dc + col * N + k];
+                    for (int r = 0; r < N; r++) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int k = 0; k < N; k++) acc = fmaf(minv_sym(s, r, k), dcol[k], acc);
+                        s[L::dc + col * N + r] = -acc;
+                    }
+                }
+                __syncthreads();
+                for (int e = tid; e < 2 * N * N; e += NT) o[e] = s[L::dc + e];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}}  // namespace GRID_NS::wps
+
+namespace GRID_NS { namespace wps {
+
+template <int ALG, bool EXTRA>
+cudaError_t wps_launch(float *d_out, const float *d_in, int stride, const float *d_qdd, const float *d_Minv,
+                       int num_states, float gravity, cudaStream_t stream) {
+    if (num_states <= 0) return cudaSuccess;
+    auto kern = wps_kernel<ALG, EXTRA>;
+    constexpr size_t smem_bytes = sizeof(float) * L::total;
+    static int cap = 0;
+    if (cap == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem_bytes);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        cap = sms * per_sm;
+    }
+    const int blocks = num_states < cap ? num_states : cap;
+    kern<<<blocks, NT, smem_bytes, stream>>>(d_out, d_in, stride, d_qdd, d_Minv, num_states, gravity);
+    return cudaGetLastError();
+}
+
+}}  // namespace GRID_NS::wps

@@ -1,5 +1,7 @@
 """GPU parity proper: the CUDA path, called through the C ABI, against the oracle on seeded
 states and against the committed reference goldens."""
+import os
+
 import numpy as np
 import pytest
 
@@ -14,6 +16,25 @@ from gridcodegenerator_b200.synthetic import make_states, pack_q_qd, pack_q_qd_u
 from oracle import rbd_numpy as O                                       # noqa: E402
 
 ALL = ("id", "minv", "fd", "id_grad", "fd_grad")
+FAMILIES = ("tps", "wps")
+
+
+class forced:
+    """Pins the kernel family through the library's GRID_FORCE_KERNEL switch."""
+
+    def __init__(self, family):
+        self.family = family
+
+    def __enter__(self):
+        self.old = os.environ.get("GRID_FORCE_KERNEL")
+        if self.family:
+            os.environ["GRID_FORCE_KERNEL"] = self.family
+
+    def __exit__(self, *exc):
+        if self.old is None:
+            os.environ.pop("GRID_FORCE_KERNEL", None)
+        else:
+            os.environ["GRID_FORCE_KERNEL"] = self.old
 
 
 def dev(x):
@@ -44,8 +65,9 @@ def run_alg(eng, alg, q, qd, u, qdd=None, Minv=None, compressed=False):
     return out.cpu().numpy()
 
 
-def supported(eng, alg):
-    return eng.kernel_kind(alg) != "none"
+def supported(eng, alg, family=None):
+    kind = eng.kernel_kind(alg)
+    return kind != "none" if family is None else family in kind
 
 
 @pytest.mark.parametrize("tag", ["iiwa14", "iiwa14_damped", "hyq", "atlas", "chain64"])
@@ -60,27 +82,31 @@ def test_against_reference_goldens(tag):
         "id_grad": [(dict(), colmajor_batch(z["dc_du"])), (dict(qdd=qdd), colmajor_batch(z["dc_du_qdd"]))],
         "fd_grad": [(dict(), colmajor_batch(z["df_du"]))],
     }
-    ran = 0
-    for alg, cases in checks.items():
-        if not supported(eng, alg):
-            continue
-        for kw, ref in cases:
-            out = run_alg(eng, alg, q, qd, u, **kw)
-            assert relerr(out, ref) < TOL[alg], (tag, alg, relerr(out, ref))
-            ran += 1
-    assert ran > 0
+    ran = set()
+    for family in FAMILIES:
+        for alg, cases in checks.items():
+            if not supported(eng, alg, family):
+                continue
+            for kw, ref in cases:
+                with forced(family):
+                    out = run_alg(eng, alg, q, qd, u, **kw)
+                assert relerr(out, ref) < TOL[alg], (tag, family, alg, relerr(out, ref))
+                ran.add(alg)
+    assert ran == set(ALL), "every algorithm must have a kernel for %s, got %s" % (tag, sorted(ran))
 
 
-@pytest.mark.parametrize("name,N", [("iiwa14", 256), ("hyq", 256)])
+@pytest.mark.parametrize("name,N", [("iiwa14", 256), ("hyq", 256), ("atlas", 64), ("chain64", 8)])
+@pytest.mark.parametrize("family", FAMILIES)
 @pytest.mark.parametrize("alg", ALL)
-def test_against_oracle_256_states(name, N, alg):
+def test_against_oracle_seeded_states(name, N, alg, family):
     robot = load_named_robot(name)
     eng = get_engine(robot)
-    if not supported(eng, alg):
-        pytest.skip("no kernel for %s on %s yet" % (alg, name))
+    if not supported(eng, alg, family):
+        pytest.skip("%s has no %s kernel for %s" % (name, family, alg))
     q, qd, u, qdd = make_states(robot.n, N, seed_for(name))
     q64, qd64, u64 = (x.astype(np.float64) for x in (q, qd, u))
-    out = run_alg(eng, alg, q, qd, u)
+    with forced(family):
+        out = run_alg(eng, alg, q, qd, u)
     ref = O.batch(robot, alg, q64, qd64, u64 if alg in ("fd", "fd_grad") else None)
     assert relerr(out, ref) < TOL[alg], relerr(out, ref)
     # per-state check too (a single bad state must not hide behind the tensor-wide max)
@@ -88,7 +114,9 @@ def test_against_oracle_256_states(name, N, alg):
     assert per.max() < 20 * TOL[alg], per.max()
 
 
-def test_qdd_minv_overload_and_compressed_layouts():
+@pytest.mark.parametrize("family", FAMILIES)
+def test_qdd_minv_overload_and_compressed_layouts(family, monkeypatch):
+    monkeypatch.setenv("GRID_FORCE_KERNEL", family)
     robot = load_named_robot("iiwa14")
     eng = get_engine(robot)
     n = robot.n
@@ -106,8 +134,10 @@ def test_qdd_minv_overload_and_compressed_layouts():
         assert np.array_equal(a, b), alg
 
 
+@pytest.mark.parametrize("family", FAMILIES)
 @pytest.mark.parametrize("N", [0, 1, 31, 32, 33, 1000])
-def test_ragged_and_empty_batches(N):
+def test_ragged_and_empty_batches(N, family, monkeypatch):
+    monkeypatch.setenv("GRID_FORCE_KERNEL", family)
     robot = load_named_robot("iiwa14")
     eng = get_engine(robot)
     n = robot.n
