@@ -387,6 +387,67 @@ def trace_fd_grad(robot: Robot, use_qdd_minv: bool = False) -> Program:
     return p
 
 
+# ---- extra traces used by the emitted header's _inner functions and the facade's test_* methods ----
+def trace_id_full(robot: Robot, use_qdd: bool = False) -> Program:
+    """c plus the reference's s_vaf block [v(6n) | a(6n) | f(6n)]."""
+    p = Program()
+    n = robot.n
+    q, qd = _inputs(p, n, ("q", "qd"))
+    qdd = _inputs(p, n, ("qdd",))[0] if use_qdd else None
+    g = p.inp("gravity")
+    R = rnea(SymRobot(p, robot, q), qd, qdd, g)
+    for i in range(n):
+        p.output("c", i, R.c[i])
+    for i in range(n):
+        for r in range(6):
+            p.output("vaf", 6 * i + r, R.v[i][r])
+            p.output("vaf", 6 * n + 6 * i + r, R.a[i][r])
+            p.output("vaf", 12 * n + 6 * i + r, R.f[i][r])
+    return p
+
+
+def trace_fd_finish(robot: Robot) -> Program:
+    """qdd = Minv (u - c) with Minv read symmetrically from its upper triangle
+    (algorithms/_forward_dynamics.py:21-49)."""
+    p = Program()
+    n = robot.n
+    (u,) = _inputs(p, n, ("u",))
+    c = [p.inp("c%d" % i) for i in range(n)]
+    Mi = {(r, cc): p.inp("Minv%d" % (cc * n + r)) for r in range(n) for cc in range(r, n)}
+    umc = [u[i] - c[i] for i in range(n)]
+    for i in range(n):
+        p.output("qdd", i, dot([minv_get(Mi, i, j) for j in range(n)], umc))
+    return p
+
+
+def trace_id_grad_from_vaf(robot: Robot) -> Program:
+    """dc_du from (q, qd, v, a, f) - the reference's inverse_dynamics_gradient_inner contract
+    (algorithms/_inverse_dynamics_gradient.py:27-41).  X a_parent is recovered from a_i:
+    mxS(X a_p) = mxS(a_i - mxS(v_i) qd_i) because mxS_k(e_k) = 0."""
+    p = Program()
+    n = robot.n
+    q, qd = _inputs(p, n, ("q", "qd"))
+    sr = SymRobot(p, robot, q)
+    R = RneaResult()
+    R.v = [[p.inp("vaf%d" % (6 * i + r)) for r in range(6)] for i in range(n)]
+    R.a = [[p.inp("vaf%d" % (6 * n + 6 * i + r)) for r in range(6)] for i in range(n)]
+    R.f = [[p.inp("vaf%d" % (12 * n + 6 * i + r)) for r in range(6)] for i in range(n)]
+    R.Iv = [sr.I_mul(i, R.v[i]) for i in range(n)]
+    R.Xa = []
+    for i in range(n):
+        if robot.parent[i] >= 0:
+            R.Xa.append(vsub(R.a[i], cross_motion_axis(p, robot.S_ind[i], R.v[i], qd[i])))
+        else:
+            R.Xa.append(list(R.a[i]))
+    R.c = None
+    for j, cq, cqd in rnea_grad_columns(sr, qd, R):
+        for i in range(n):
+            p.output("dc_du", n * j + i, cq.get(i, 0.0))
+        for i in range(n):
+            p.output("dc_du", n * n + n * j + i, cqd.get(i, 0.0))
+    return p
+
+
 TRACERS = {
     "id": lambda robot: trace_id(robot, False),
     "id_qdd": lambda robot: trace_id(robot, True),

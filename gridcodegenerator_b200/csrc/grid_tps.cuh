@@ -41,31 +41,40 @@ __device__ __forceinline__ void tile_load(float *sw, int word_off, const float *
     }
 }
 
-// One warp = one tile of 32 consecutive states.  All warps of a CTA run the loop the same
-// number of times (a warp without a tile computes on stale data and stores nothing), because
-// the traced program may contain CTA-wide barriers: they keep the warps of an SM on the same
-// instruction-cache lines of the long straight-line program.
-template <class A, int WARPS, int MIN_BLOCKS>
-__global__ void __launch_bounds__(32 * WARPS, MIN_BLOCKS)
-tps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0,
-           const float *__restrict__ d_in1, const float *__restrict__ d_in2, int num_states, float gravity) {
+// One warp = one tile of 32 consecutive states.  Works for any 1-D/2-D launch shape: warps
+// beyond the dynamic shared memory that was provided (32*max(IN_PAD,OUT_PAD) floats per warp)
+// and partial warps take no tiles.  All warps of a CTA run the loop the same number of times
+// (a warp without a tile computes on stale data and stores nothing), because the traced
+// program may contain CTA-wide barriers.
+template <class A>
+__device__ __forceinline__ void tps_body(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0,
+                                         const float *__restrict__ d_in1, const float *__restrict__ d_in2,
+                                         int num_states, float gravity) {
     using S = TpsShape<A>;
     extern __shared__ float smem[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    float *sw = smem + warp * S::WARP_WORDS;
+    unsigned smem_bytes;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(smem_bytes));
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int full_warps = (blockDim.x * blockDim.y * blockDim.z) >> 5;
+    const int warps = min(full_warps, (int)(smem_bytes / (sizeof(float) * S::WARP_WORDS)));
+    const bool worker = warp < warps;
+    float *sw = smem + (worker ? warp : 0) * S::WARP_WORDS;
     const int ntiles = (num_states + 31) >> 5;
-    for (int tile0 = blockIdx.x * WARPS; tile0 < ntiles; tile0 += gridDim.x * WARPS) {
+    const int nblocks = gridDim.x * gridDim.y, block = blockIdx.x + blockIdx.y * gridDim.x;
+    if (warps == 0) return;
+    for (int tile0 = block * warps; tile0 < ntiles; tile0 += nblocks * warps) {
         const int tile = tile0 + warp;
         const long long first = (long long)tile * 32;
-        const int cnt = max(0, min(32, num_states - (int)first));
+        const int cnt = worker ? max(0, min(32, num_states - (int)first)) : 0;
         tile_load<A::IN0, S::IN_PAD>(sw, 0, d_in0, first, stride0, cnt, lane);
         tile_load<A::IN1, S::IN_PAD>(sw, A::IN0, d_in1, first, A::IN1, cnt, lane);
         tile_load<A::IN2, S::IN_PAD>(sw, A::IN0 + A::IN1, d_in2, first, A::IN2, cnt, lane);
         __syncwarp();
         // lanes past the end of a ragged tile recompute the last valid state (results dropped)
         const int src = max(0, min(lane, cnt - 1));
-        A::eval(sw + src * S::IN_PAD, sw + lane * S::OUT_PAD, gravity);
+        if (worker) A::eval(sw + src * S::IN_PAD, sw + lane * S::OUT_PAD, gravity);
         __syncwarp();
         float *dst = d_out + first * A::OUT;
         for (int e = lane; e < cnt * A::OUT; e += 32) {
@@ -74,6 +83,13 @@ tps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int strid
         }
         __syncwarp();
     }
+}
+
+template <class A, int WARPS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(32 * WARPS, MIN_BLOCKS)
+tps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0,
+           const float *__restrict__ d_in1, const float *__restrict__ d_in2, int num_states, float gravity) {
+    tps_body<A>(d_out, d_in0, stride0, d_in1, d_in2, num_states, gravity);
 }
 
 template <class A, int WARPS, int MIN_BLOCKS>

@@ -1,0 +1,107 @@
+// Exercises an emitted <namespace>.cuh the way a GRiD-wrapper user would: init_*, fill h_*,
+// call the host functions, read h_* back; plus one kernel that calls the _inner/_device
+// functions on state 0.  argv: <input.bin> <output.bin>
+// input : int32 N, float q_qd_u[N*3n], float qdd[N*n]
+// output: c, c_qdd, Minv, fd_qdd, dc_du, dc_du_qdd, df_du, df_du_pre, df_du_compute_only  (N states each)
+//         then device-function results for state 0: df_du_dev, dc_du_inner, Minv_inner, qdd_finish, c_inner
+#include "grid.cuh"
+#include <vector>
+using namespace grid;
+
+#ifdef HARNESS_DEVICE_FNS
+template <typename T>
+__global__ void device_fn_kernel(T *out, const T *q_qd_u, const T *qdd_in, const T *Minv_in,
+                                 const robotModel<T> *d_robotModel, T gravity) {
+    constexpr int n = NUM_JOINTS;
+    __shared__ T s_q[n], s_qd[n], s_u[n], s_qdd[n], s_c[n], s_vaf[18 * n], s_Minv[n * n], s_out[2 * n * n], s_fin[n];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        s_q[i] = q_qd_u[i]; s_qd[i] = q_qd_u[n + i]; s_u[i] = q_qd_u[2 * n + i]; s_qdd[i] = qdd_in[i];
+    }
+    __syncthreads();
+    T *o = out;
+    forward_dynamics_gradient_device<T>(s_out, s_q, s_qd, s_u, d_robotModel, gravity);
+    for (int i = threadIdx.x; i < 2 * n * n; i += blockDim.x) o[i] = s_out[i];
+    o += 2 * n * n;
+    __syncthreads();
+    inverse_dynamics_inner<T>(s_c, s_vaf, s_q, s_qd, s_qdd, (T *)nullptr, (T *)nullptr, gravity);
+    inverse_dynamics_gradient_inner<T>(s_out, s_q, s_qd, s_vaf, (T *)nullptr, (T *)nullptr, gravity);
+    for (int i = threadIdx.x; i < 2 * n * n; i += blockDim.x) o[i] = s_out[i];
+    o += 2 * n * n;
+    __syncthreads();
+    direct_minv_inner<T>(s_Minv, s_q, (T *)nullptr, (T *)nullptr);
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) o[i] = s_Minv[i];
+    o += n * n;
+    __syncthreads();
+    // c at qdd = 0, then qdd = Minv (u - c)
+    inverse_dynamics_device<T>(s_c, s_q, s_qd, d_robotModel, gravity);
+    forward_dynamics_finish<T>(s_fin, s_u, s_c, s_Minv);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { o[i] = s_fin[i]; o[n + i] = s_c[i]; }
+}
+
+#endif
+
+int main(int argc, char **argv) {
+    if (argc < 3) { fprintf(stderr, "usage: %s in.bin out.bin\n", argv[0]); return 2; }
+    const int n = NUM_JOINTS;
+    FILE *f = fopen(argv[1], "rb");
+    if (!f) { perror("input"); return 2; }
+    int N = 0;
+    if (fread(&N, sizeof(int), 1, f) != 1) return 2;
+    std::vector<float> in(size_t(N) * 3 * n), qdd(size_t(N) * n);
+    if (fread(in.data(), sizeof(float), in.size(), f) != in.size()) return 2;
+    if (fread(qdd.data(), sizeof(float), qdd.size(), f) != qdd.size()) return 2;
+    fclose(f);
+    const float gravity = 9.81f;
+    robotModel<float> *d_robotModel = init_robotModel<float>();
+    cudaStream_t *streams = init_grid<float>();
+    gridData<float> *hd = init_gridData<float>(N);
+    dim3 blocks(N), threads(SUGGESTED_THREADS);
+    memcpy(hd->h_q_qd_u, in.data(), in.size() * sizeof(float));
+    FILE *o = fopen(argv[2], "wb");
+    auto dump = [&](const float *p, size_t words) { fwrite(p, sizeof(float), words, o); };
+
+    inverse_dynamics<float>(hd, d_robotModel, gravity, N, blocks, threads, streams);
+    dump(hd->h_c, size_t(N) * n);
+    memcpy(hd->h_qdd, qdd.data(), qdd.size() * sizeof(float));
+    inverse_dynamics<float, true>(hd, d_robotModel, gravity, N, blocks, threads, streams);
+    dump(hd->h_c, size_t(N) * n);
+    direct_minv<float>(hd, d_robotModel, N, blocks, threads, streams);
+    dump(hd->h_Minv, size_t(N) * n * n);
+    std::vector<float> Minv(hd->h_Minv, hd->h_Minv + size_t(N) * n * n);
+    forward_dynamics<float>(hd, d_robotModel, gravity, N, blocks, threads, streams);
+    dump(hd->h_qdd, size_t(N) * n);
+    std::vector<float> fd_qdd(hd->h_qdd, hd->h_qdd + size_t(N) * n);
+    inverse_dynamics_gradient<float>(hd, d_robotModel, gravity, N, blocks, threads, streams);
+    dump(hd->h_dc_du, size_t(N) * 2 * n * n);
+    memcpy(hd->h_qdd, qdd.data(), qdd.size() * sizeof(float));
+    inverse_dynamics_gradient<float, true>(hd, d_robotModel, gravity, N, blocks, threads, streams);
+    dump(hd->h_dc_du, size_t(N) * 2 * n * n);
+    forward_dynamics_gradient<float>(hd, d_robotModel, gravity, N, blocks, threads, streams);
+    dump(hd->h_df_du, size_t(N) * 2 * n * n);
+    // USE_QDD_MINV_FLAG: feed FD's own qdd and Minv back in
+    memcpy(hd->h_qdd, fd_qdd.data(), fd_qdd.size() * sizeof(float));
+    memcpy(hd->h_Minv, Minv.data(), Minv.size() * sizeof(float));
+    forward_dynamics_gradient<float, true>(hd, d_robotModel, gravity, N, blocks, threads, streams);
+    dump(hd->h_df_du, size_t(N) * 2 * n * n);
+    // compute-only: inputs are already on the device from the previous call
+    gpuErrchk(cudaMemset(hd->d_df_du, 0, size_t(N) * 2 * n * n * sizeof(float)));
+    forward_dynamics_gradient_compute_only<float>(hd, d_robotModel, gravity, N, blocks, threads);
+    gpuErrchk(cudaMemcpy(hd->h_df_du, hd->d_df_du, size_t(N) * 2 * n * n * sizeof(float), cudaMemcpyDeviceToHost));
+    dump(hd->h_df_du, size_t(N) * 2 * n * n);
+
+#ifdef HARNESS_DEVICE_FNS
+    const size_t dev_words = 2 * n * n * 2 + n * n + 2 * n;
+    float *d_dev;
+    gpuErrchk(cudaMalloc(&d_dev, dev_words * sizeof(float)));
+    device_fn_kernel<float><<<1, 64>>>(d_dev, hd->d_q_qd_u, hd->d_qdd, hd->d_Minv, d_robotModel, gravity);
+    gpuErrchk(cudaDeviceSynchronize());
+    std::vector<float> dev(dev_words);
+    gpuErrchk(cudaMemcpy(dev.data(), d_dev, dev_words * sizeof(float), cudaMemcpyDeviceToHost));
+    dump(dev.data(), dev_words);
+    cudaFree(d_dev);
+#endif
+    fclose(o);
+    close_grid<float>(streams, d_robotModel, hd);
+    printf("ok N=%d n=%d\n", N, n);
+    return 0;
+}

@@ -1,0 +1,140 @@
+"""The drop-in Python surface: same method names as the reference class, numpy test_* methods,
+gen_all_code() writes a header that nvcc accepts for sm_100a; on the GPU the header's host
+functions and _inner/_device functions are checked against the oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from gridcodegenerator_b200 import GRiDCodeGenerator, load_named_robot
+from gridcodegenerator_b200.synthetic import make_states, pack_q_qd_u
+from helpers import TOL, relerr
+from oracle import rbd_numpy as O
+
+# pass-level debug helpers of _test.py that the facade does not provide
+NOT_PROVIDED = {"test_rnea_fpass", "test_rnea_bpass", "test_minv_bpass", "test_minv_fpass", "test_rnea_grad_inner"}
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/GRiDCodeGenerator.py"), reason="reference tree not present")
+def test_every_public_reference_method_exists():
+    sys.path.insert(0, "/root")
+    from reference import GRiDCodeGenerator as Ref
+    ref_names = {n for n in dir(Ref) if n.startswith(("gen_", "test_", "mx", "fx"))}
+    mine = set(dir(GRiDCodeGenerator))
+    assert ref_names - mine - NOT_PROVIDED == set()
+
+
+def test_constructor_and_sizes():
+    g = GRiDCodeGenerator(load_named_robot("iiwa14"), DEBUG_MODE=False, FILE_NAMESPACE="grid")
+    assert g.file_namespace == "grid" and g.indent_level == 0 and g.code_str == ""
+    for alg in ("inverse_dynamics", "direct_minv", "forward_dynamics", "inverse_dynamics_gradient",
+                "forward_dynamics_gradient"):
+        assert getattr(g, "gen_%s_inner_temp_mem_size" % alg)() == 0       # no shared scratch is needed
+    dva, dva_per, run_dva, df, df_per, run_df, col = g.gen_topology_sparsity_helpers_python()
+    assert dva == 28 and df == 49 and dva_per == [1, 2, 3, 4, 5, 6, 7]
+
+
+def test_emitter_helpers_append_to_code_str():
+    g = GRiDCodeGenerator(load_named_robot("iiwa14"))
+    g.gen_add_code_line("int x = 0;")
+    g.gen_add_parallel_loop("ind", "7")
+    g.gen_add_code_line("x += ind;")
+    g.gen_add_end_control_flow()
+    g.gen_add_sync()
+    assert g.code_str == ("int x = 0;\nfor(int ind = threadIdx.x + threadIdx.y*blockDim.x; ind < 7; "
+                          "ind += blockDim.x*blockDim.y){\n    x += ind;\n}\n__syncthreads();\n")
+    g.gen_forward_dynamics_finish_function_call()
+    assert "forward_dynamics_finish<T>(s_qdd, s_u, s_c, s_Minv);" in g.code_str
+
+
+@pytest.mark.parametrize("name", ["iiwa14", "hyq"])
+def test_numpy_test_methods_match_oracle(name):
+    robot = load_named_robot(name).with_damping(0.2)
+    g = GRiDCodeGenerator(robot)
+    q, qd, u, qdd = (x[0].astype(np.float64) for x in make_states(robot.n, 1, 4))
+    c, v, a, f = g.test_rnea(q, qd, qdd)
+    co, vo, ao, fo = O.rnea(robot, q, qd, qdd)
+    assert relerr(c, co) < 1e-12 and relerr(v, vo) < 1e-12 and relerr(a, ao) < 1e-12 and relerr(f, fo) < 1e-12
+    assert relerr(g.test_rnea(q, qd)[0], O.rnea(robot, q, qd)[0]) < 1e-12
+    assert relerr(g.test_minv(q), O.minv(robot, q)) < 1e-12
+    assert relerr(g.test_minv(q, output_dense=False), O.minv(robot, q, dense=False)) < 1e-12
+    assert relerr(g.test_rnea_grad(q, qd, qdd), O.rnea_grad(robot, q, qd, qdd)) < 1e-11
+    assert relerr(g.test_fd_grad(q, qd, u), O.fd_grad(robot, q, qd, u)) < 1e-10
+    S = robot.get_S_by_id(0)
+    assert np.allclose(g.mxS(S, v[:, 1], 0.5), O.cross_motion_axis(robot.S_ind[0], v[:, 1], 0.5))
+    assert np.allclose(g.fxv(v[:, 1], f[:, 1]), O.cross_force(v[:, 1], f[:, 1]))
+
+
+def test_gen_all_code_writes_header_with_reference_contract(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    g = GRiDCodeGenerator(load_named_robot("hyq"), FILE_NAMESPACE="hyqgrid")
+    assert g.gen_all_code() is None
+    text = (tmp_path / "hyqgrid.cuh").read_text()
+    for needle in ("namespace hyqgrid {", "const int NUM_JOINTS = 12;", "struct robotModel {", "struct gridData {",
+                   "robotModel<T>* init_robotModel()", "cudaStream_t *init_grid()", "gridData<T> *init_gridData(",
+                   "void close_grid(cudaStream_t *streams, robotModel<T> *d_robotModel, gridData<T> *hd_data)",
+                   "void inverse_dynamics_inner(T *s_c, T *s_vaf, const T *s_q, const T *s_qd, const T *s_qdd, ",
+                   "void direct_minv_device(T *s_Minv, const T *s_q, const robotModel<T> *d_robotModel)",
+                   "void forward_dynamics_kernel(T *d_qdd, const T *d_q_qd_u, const int stride_q_qd_u, ",
+                   "void inverse_dynamics_gradient_kernel(T *d_dc_du, const T *d_q_qd, const int stride_q_qd, const T *d_qdd, ",
+                   "void forward_dynamics_gradient(gridData<T> *hd_data, const robotModel<T> *d_robotModel, const T gravity, "
+                   "const int num_timesteps, const dim3 block_dimms, const dim3 thread_dimms, cudaStream_t *streams)",
+                   "void forward_dynamics_gradient_compute_only(", "void inverse_dynamics_single_timing(",
+                   "FD_DU_DYNAMIC_SHARED_MEM_COUNT", "SUGGESTED_THREADS"):
+        assert needle in text, needle
+
+
+def test_emitted_header_compiles_for_sm100a():
+    from gridcodegenerator_b200.header_build import build_header_harness
+    exe = build_header_harness("iiwa14")
+    assert os.path.exists(exe)
+    out = subprocess.run(["cuobjdump", "-lelf", exe], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+@pytest.mark.gpu
+def test_emitted_header_host_and_device_functions_on_gpu(tmp_path):
+    from gridcodegenerator_b200.header_build import build_header_harness
+    robot = load_named_robot("iiwa14")
+    n, N = robot.n, 200
+    exe = build_header_harness("iiwa14")
+    q, qd, u, qdd = make_states(n, N, 21)
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(np.int32(N).tobytes())
+        f.write(pack_q_qd_u(q, qd, u).tobytes())
+        f.write(np.ascontiguousarray(qdd).tobytes())
+    proc = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True,
+                          timeout=120)
+    assert proc.returncode == 0, proc.stdout + proc.stderr
+    data = np.fromfile(tmp_path / "out.bin", dtype=np.float32)
+    pos = 0
+
+    def take(words_per_state, states=N):
+        nonlocal pos
+        x = data[pos:pos + words_per_state * states].reshape(states, words_per_state)
+        pos += words_per_state * states
+        return x
+
+    q64, qd64, u64, qdd64 = (x.astype(np.float64) for x in (q, qd, u, qdd))
+    S = slice(0, 24)           # oracle sample
+    ref_fd_grad = O.batch(robot, "fd_grad", q64[S], qd64[S], u64[S])
+    assert relerr(take(n)[S], O.batch(robot, "id", q64[S], qd64[S])) < TOL["id"]
+    assert relerr(take(n)[S], O.batch(robot, "id", q64[S], qd64[S], qdd64[S])) < TOL["id"]
+    assert relerr(take(n * n)[S], O.batch(robot, "minv", q64[S])) < TOL["minv"]
+    assert relerr(take(n)[S], O.batch(robot, "fd", q64[S], qd64[S], u64[S])) < TOL["fd"]
+    assert relerr(take(2 * n * n)[S], O.batch(robot, "id_grad", q64[S], qd64[S])) < TOL["id_grad"]
+    assert relerr(take(2 * n * n)[S], O.batch(robot, "id_grad", q64[S], qd64[S], qdd64[S])) < TOL["id_grad"]
+    df = take(2 * n * n)
+    assert relerr(df[S], ref_fd_grad) < TOL["fd_grad"]
+    assert relerr(take(2 * n * n)[S], ref_fd_grad) < TOL["fd_grad"]          # USE_QDD_MINV_FLAG
+    assert np.array_equal(take(2 * n * n), df)                                # _compute_only
+    # device functions on state 0 (the last host call left FD's qdd in d_qdd)
+    assert relerr(take(2 * n * n, 1)[0], ref_fd_grad[0]) < TOL["fd_grad"]    # forward_dynamics_gradient_device
+    fdq = O.fd(robot, q64[0], qd64[0], u64[0])
+    assert relerr(take(2 * n * n, 1)[0], O.colmajor(O.rnea_grad(robot, q64[0], qd64[0], fdq))) < TOL["id_grad"]
+    assert relerr(take(n * n, 1)[0], O.colmajor(O.minv(robot, q64[0], dense=False))) < TOL["minv"]
+    assert relerr(take(n, 1)[0], fdq) < TOL["fd"]                              # forward_dynamics_finish
+    assert relerr(take(n, 1)[0], O.rnea(robot, q64[0], qd64[0])[0]) < TOL["id"]
+    assert pos == data.size
