@@ -377,9 +377,27 @@ class GRiDCodeGenerator:
                                  "const robotModel<T> *d_robotModel, T *s_temp) {}", ""])
 
     def gen_init_close_grid(self):
-        self.gen_add_func_doc("Initializes streams for host functions", [], [], "A pointer to the array of streams")
+        if self._unsupported & {"id_grad", "fd_grad"}:
+            self.gen_add_code_line("// gradient kernels are not part of this header build (robot too large for the "
+                                   "single-thread programs); use libgrid_<robot>.so")
+            return
+        self.gen_add_func_doc("Sets shared mem needed for gradient kernels and initializes streams for host functions",
+                              [], [], "A pointer to the array of streams")
         self.gen_add_code_lines([
             "template <typename T>", "__host__", "cudaStream_t *init_grid(){",
+            "    // the gradient kernels may need more than the default 48 KB of dynamic shared memory",
+            "    typedef void (*k6_t)(T *, const T *, const int, const robotModel<T> *, const T, const int);",
+            "    typedef void (*k7_t)(T *, const T *, const int, const T *, const robotModel<T> *, const T, const int);",
+            "    typedef void (*k8_t)(T *, const T *, const int, const T *, const T *, const robotModel<T> *, const T, const int);",
+            "    const int id_du_bytes = ID_DU_MAX_SHARED_MEM_COUNT*sizeof(T), fd_du_bytes = FD_DU_MAX_SHARED_MEM_COUNT*sizeof(T);",
+            "    gpuErrchk(cudaFuncSetAttribute(static_cast<k6_t>(&inverse_dynamics_gradient_kernel<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,id_du_bytes));",
+            "    gpuErrchk(cudaFuncSetAttribute(static_cast<k7_t>(&inverse_dynamics_gradient_kernel<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,id_du_bytes));",
+            "    gpuErrchk(cudaFuncSetAttribute(static_cast<k6_t>(&inverse_dynamics_gradient_kernel_single_timing<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,id_du_bytes));",
+            "    gpuErrchk(cudaFuncSetAttribute(static_cast<k7_t>(&inverse_dynamics_gradient_kernel_single_timing<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,id_du_bytes));",
+            "    gpuErrchk(cudaFuncSetAttribute(static_cast<k6_t>(&forward_dynamics_gradient_kernel<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,fd_du_bytes));",
+            "    gpuErrchk(cudaFuncSetAttribute(static_cast<k8_t>(&forward_dynamics_gradient_kernel<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,fd_du_bytes));",
+            "    gpuErrchk(cudaFuncSetAttribute(static_cast<k6_t>(&forward_dynamics_gradient_kernel_single_timing<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,fd_du_bytes));",
+            "    gpuErrchk(cudaFuncSetAttribute(static_cast<k8_t>(&forward_dynamics_gradient_kernel_single_timing<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,fd_du_bytes));",
             "    cudaStream_t *streams = (cudaStream_t *)malloc(3*sizeof(cudaStream_t));",
             "    int minPriority, maxPriority; gpuErrchk(cudaDeviceGetStreamPriorityRange(&minPriority, &maxPriority));",
             "    for(int i=0; i<3; i++){ gpuErrchk(cudaStreamCreateWithPriority(&(streams[i]),cudaStreamNonBlocking,maxPriority)); }",
@@ -552,7 +570,7 @@ class GRiDCodeGenerator:
         lines += ["    " + k.replace("KERNEL<T>", ("%s_kernel%s<T>" % (fn, "_single_timing" if single else "")))
                   .replace("<<<>>>", "<<<blocks_,SUGGESTED_THREADS,smem_>>>")
                   .replace("NT_", "num_timesteps") for k in kernel_calls]
-        lines.append("    gpuErrchk(cudaDeviceSynchronize());")
+        lines.append("    gpuErrchk(cudaGetLastError()); gpuErrchk(cudaDeviceSynchronize());")
         if single:
             lines.append("    clock_gettime(CLOCK_MONOTONIC,&end);")
         if not compute_only:
