@@ -265,16 +265,11 @@ def run_b200_arm(a):
     lat = None
     if rank == 0:
         small_in, small_out = ins[0][:128], outs[0][:128]
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(300)]
-        for s, e in evs:
-            s.record(stream)
-            eng.forward_dynamics_gradient_device(small_out, small_in, num_timesteps=128, stride=3 * n, stream=stream) \
-                if a.alg == "fd_grad" else step(0)
-            e.record(stream)
-        torch.cuda.synchronize()
-        us = np.array([s.elapsed_time(e) * 1e3 for s, e in evs[50:]])
+        us = eng.time_launches(a.alg, small_out, small_in, num_timesteps=128, stride=3 * n, reps=500)
         lat = {"p50_us": float(np.percentile(us, 50)), "p90_us": float(np.percentile(us, 90)),
-               "min_us": float(us.min()), "what": "%s N=128 single launch, CUDA events around the launch" % a.alg}
+               "min_us": float(us.min()), "kernel": eng.kernel_kind(a.alg),
+               "what": "%s N=128, one CUDA event pair per launch recorded in C (grid_time_launches), 500 launches "
+                       "queued back to back" % a.alg}
 
     if rank != 0:
         if world > 1:

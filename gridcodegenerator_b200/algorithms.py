@@ -448,6 +448,69 @@ def trace_id_grad_from_vaf(robot: Robot) -> Program:
     return p
 
 
+# ---- lane-uniform column program (latency kernels, csrc/grid_cps.cuh) -------------------------
+def rnea_grad_generic_column(sr: SymRobot, qd: Sequence[V], R: RneaResult, mq: Sequence[V], mqd: Sequence[V]):
+    """One du-column of dc_du written so that EVERY column runs the same instruction stream:
+    mq[i] / mqd[i] are 0/1 values selecting "this column is d/dq_i" / "d/dqd_i".  All joints are
+    visited; columns that do not reach a joint carry exact zeros through it.  Returns dc[0..n)."""
+    p, robot, n = sr.p, sr.robot, sr.n
+    dv: List[List[V]] = [None] * n
+    da: List[List[V]] = [None] * n
+    df: List[List[V]] = [None] * n
+    for i in range(n):
+        k, par = robot.S_ind[i], robot.parent[i]
+        ek = zeros(p, 6)
+        ek[k] = p.const(1.0)
+        mv = cross_motion_axis(p, k, R.v[i])
+        sdv = vadd(vscale(mv, mq[i]), vscale(ek, mqd[i]))
+        sda = vadd(vscale(cross_motion_axis(p, k, R.Xa[i]), mq[i]), vscale(mv, mqd[i]))
+        if par >= 0:
+            dv[i] = vadd(sr.X_motion(i, dv[par]), sdv)
+            da[i] = vadd(vadd(sr.X_motion(i, da[par]), cross_motion_axis(p, k, dv[i], qd[i])), sda)
+        else:
+            dv[i] = sdv
+            da[i] = vadd(cross_motion_axis(p, k, dv[i], qd[i]), sda)
+        df[i] = vadd(vadd(sr.I_mul(i, da[i]), cross_force(dv[i], R.Iv[i])),
+                     cross_force(R.v[i], sr.I_mul(i, dv[i])))
+    dc: List[V] = [None] * n
+    for i in range(n - 1, -1, -1):
+        k, par = robot.S_ind[i], robot.parent[i]
+        dc[i] = df[i][k] + mqd[i] * robot.damping[i]
+        if par >= 0:
+            leaving = vsub(df[i], vscale(cross_motion_axis(p, k, R.f[i]), mq[i]))
+            df[par] = vadd(df[par], sr.XT_force(i, leaving))
+    return dc
+
+
+def trace_column_program(robot: Robot, alg: str, use_qdd: bool = False) -> Program:
+    """alg = "id_grad": inputs (q, qd[, qdd], masks) -> col[0..n) = dc_du[:, column];
+    alg = "fd_grad": inputs (q, qd, u, masks) -> col = -Minv dc_du[:, column]."""
+    p = Program()
+    n = robot.n
+    q, qd = _inputs(p, n, ("q", "qd"))
+    g = p.inp("gravity")
+    sr = SymRobot(p, robot, q)
+    Mi = None
+    if alg == "fd_grad":
+        (u,) = _inputs(p, n, ("u",))
+        R0 = rnea(sr, qd, None, g)
+        Mi = minv(sr)
+        umc = [u[i] - R0.c[i] for i in range(n)]
+        qdd = [dot([minv_get(Mi, i, j) for j in range(n)], umc) for i in range(n)]
+    else:
+        qdd = _inputs(p, n, ("qdd",))[0] if use_qdd else None
+    R = rnea(sr, qd, qdd, g)
+    mq = [p.inp("mq%d" % i) for i in range(n)]
+    mqd = [p.inp("mqd%d" % i) for i in range(n)]
+    dc = rnea_grad_generic_column(sr, qd, R, mq, mqd)
+    for i in range(n):
+        if Mi is None:
+            p.output("col", i, dc[i])
+        else:
+            p.output("col", i, -dot([minv_get(Mi, i, r) for r in range(n)], dc))
+    return p
+
+
 TRACERS = {
     "id": lambda robot: trace_id(robot, False),
     "id_qdd": lambda robot: trace_id(robot, True),

@@ -121,6 +121,69 @@ def emit_eval(p: Program, n: int, in0_words: int, in1_words: int, out_name: str,
     return lines + body, p.op_counts()
 
 
+def emit_col_struct(robot: Robot, name: str, alg: str, use_qdd: bool = False) -> Tuple[str, Dict[str, int]]:
+    """Lane-uniform column program (algorithms.trace_column_program) as a struct for csrc/grid_cps.cuh:
+    inputs straight from global memory (all lanes of a state read the same row: broadcast), masks
+    from the lane's column index, each lane stores its own column."""
+    from .algorithms import trace_column_program
+    n = robot.n
+    p = trace_column_program(robot, alg, use_qdd)
+    live = p.live_nodes()
+    in0 = 3 * n if alg == "fd_grad" else 2 * n
+    in1 = n if use_qdd else 0
+    L = ["struct %s {" % name,
+         "    static constexpr int IN0 = %d, IN1 = %d, COLS = %d, ROWS = %d;" % (in0, max(in1, 1), 2 * n, n),
+         "    static __device__ __forceinline__ void eval(const float *__restrict__ g_in, const float *__restrict__ g_in1,"
+         " float *__restrict__ g_out, const int col, const bool wr, const float gravity) {"]
+    ind = "        "
+    outs: Dict[int, list] = {}
+    for (_, idx, v) in p.outputs:
+        outs.setdefault(-1 if v.is_const else v.i, []).append((idx, v))
+    for idx, v in outs.get(-1, []):
+        L.append("%sif (wr) g_out[%d] = %s;" % (ind, idx, _flit(v.c)))
+    done = set()
+    for i, k in enumerate(p.nodes):
+        if not live[i]:
+            continue
+        op = k[0]
+        if op == "in":
+            nm = k[1]
+            if nm == "gravity":
+                L.append("%sconst float t%d = gravity;" % (ind, i))
+            elif nm.startswith("mqd"):
+                L.append("%sconst float t%d = (col == %d) ? 1.0f : 0.0f;" % (ind, i, n + int(nm[3:])))
+            elif nm.startswith("mq"):
+                L.append("%sconst float t%d = (col == %d) ? 1.0f : 0.0f;" % (ind, i, int(nm[2:])))
+            elif nm.startswith("qdd"):
+                L.append("%sconst float t%d = __ldg(g_in1 + %d);" % (ind, i, int(nm[3:])))
+            else:
+                m = _NAME_RE.match(nm)
+                kind, idx = m.group(1), int(m.group(2))
+                L.append("%sconst float t%d = __ldg(g_in + %d);" % (ind, i, {"q": 0, "qd": n, "u": 2 * n}[kind] + idx))
+        elif op in ("sin", "cos"):
+            a = k[1]
+            if a not in done:
+                done.add(a)
+                si, ci = p._cse.get(("sin", a)), p._cse.get(("cos", a))
+                sn = "t%d" % si if si is not None and live[si] else "us%d" % a
+                cn = "t%d" % ci if ci is not None and live[ci] else "uc%d" % a
+                L.append("%sfloat %s, %s; sincosf(t%d, &%s, &%s);" % (ind, sn, cn, a, sn, cn))
+        elif op == "rcp":
+            L.append("%sconst float t%d = 1.0f / t%d;" % (ind, i, k[1]))
+        elif op == "mul":
+            L.append("%sconst float t%d = t%d * t%d;" % (ind, i, k[1], k[2]))
+        elif op == "mulc":
+            L.append("%sconst float t%d = t%d * %s;" % (ind, i, k[1], _flit(k[2])))
+        elif op == "add":
+            L.append("%sconst float t%d = t%d %s t%d;" % (ind, i, k[1], "+" if k[3] > 0 else "-", k[2]))
+        elif op == "addc":
+            L.append("%sconst float t%d = t%d + %s;" % (ind, i, k[1], _flit(k[2])))
+        for idx, v in outs.get(i, []):
+            L.append("%sif (wr) g_out[%d] = %st%d;" % (ind, idx, "-" if v.s < 0 else "", v.i))
+    L += ["    }", "};", ""]
+    return "\n".join(L), p.op_counts()
+
+
 def emit_alg_struct(robot: Robot, variant: str, p: Optional[Program] = None,
                     sync_every: int = 0) -> Tuple[str, Dict[str, int]]:
     n = robot.n
@@ -237,7 +300,7 @@ class KernelPlan:
 
     def __init__(self, robot: Robot, tps_max_flops: int = 60000, tps_warps: int = 1,
                  tps_min_blocks: Optional[Dict[str, int]] = None, tps_sync_every: int = 0,
-                 wps_max_states: int = 1024):
+                 wps_max_states: int = 0, cps_max_states: int = 2048):
         self.robot = robot
         self.tps_warps = tps_warps
         self.tps_sync_every = tps_sync_every if tps_warps > 1 else 0
@@ -252,6 +315,11 @@ class KernelPlan:
             tps = alg[a] <= tps_max_flops
             wps = self.wps_ok and a != "id"
             self.kind[a] = "tps+wps" if tps and wps else "tps" if tps else "wps" if wps else "none"
+            # latency kernels: gradient algorithms of robots whose 2n columns fit one warp
+            if tps and a in ("id_grad", "fd_grad") and 2 * robot.n <= 32:
+                self.kind[a] += "+cps"
+        self.cps_lanes = 16 if 2 * robot.n <= 16 else 32
+        self.cps_max_states = cps_max_states
         # resident single-warp CTAs per SM = register cap 65536/(32*min_blocks).  Measured on B200
         # (profiles/r1_sweep_tps.md): the gradient programs spill at 128/168 registers and run
         # 2.1x faster at 255 registers with no spills; the small programs fit 128.
@@ -302,7 +370,16 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
             txt, cnt = emit_alg_struct(robot, v, sync_every=plan.tps_sync_every)
             out.append(txt)
             stats[v] = cnt
+    has_cps = any("cps" in k for k in plan.kind.values())
+    if has_cps:
+        for nm, alg, uq in (("ColIdGrad", "id_grad", False), ("ColIdGradQdd", "id_grad", True),
+                            ("ColFdGrad", "fd_grad", False)):
+            txt, cnt = emit_col_struct(robot, nm, alg, uq)
+            out.append(txt)
+            stats["cps_" + nm] = cnt
     out.append("}}  // namespace GRID_NS::gen\n")
+    if has_cps:
+        out.append('#include "grid_cps.cuh"\n')
 
     W = plan.tps_warps
     has_tps = lambda a: "tps" in plan.kind[a]
@@ -313,9 +390,13 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
     def tps(a, struct):
         return "tps_launch<%s, %d, %d>" % (struct, W, plan.min_blocks[a])
 
-    def body(a, tps_call, wps_call):
-        """tps_call / wps_call: list of (condition or None, expression)."""
+    def body(a, tps_call, wps_call, cps_call=()):
+        """tps_call / wps_call / cps_call: list of (condition or None, expression)."""
         lines = []
+        if "cps" in plan.kind[a]:
+            lines.append("    if (use_cps(N)) {")
+            lines += ["        %sreturn %s;" % ("if (%s) " % c if c else "", e) for c, e in cps_call]
+            lines.append("    }")
         if has_tps(a) and has_wps(a):
             lines.append("    if (use_wide(N)) {")
             lines += ["        %sreturn %s;" % ("if (%s) " % c if c else "", e) for c, e in wps_call]
@@ -337,6 +418,12 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
              "    if (f && !strcmp(f, \"wps\")) return true;\n"
              "    if (f && !strcmp(f, \"tps\")) return false;\n"
              "    return N <= %d;\n}" % plan.wps_max_states)
+    L.append("// small batches go to the lane-per-column latency kernels\n"
+             "static bool use_cps(int N) {\n"
+             "    const char *f = getenv(\"GRID_FORCE_KERNEL\");\n"
+             "    if (f) return !strcmp(f, \"cps\");\n"
+             "    return N <= %d;\n}" % plan.cps_max_states)
+    G = plan.cps_lanes
     L.append("cudaError_t launch_id(float *d_c, const float *d_q_qd, int stride, const float *d_qdd, int N, float g,"
              " cudaStream_t s) {")
     L += body("id", [("d_qdd", "%s(d_c, d_q_qd, stride, d_qdd, nullptr, N, g, s)" % tps("id", "AlgIdQdd")),
@@ -356,7 +443,9 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
               [("d_qdd", "%s(d_dc_du, d_q_qd, stride, d_qdd, nullptr, N, g, s)" % tps("id_grad", "AlgIdGradQdd")),
                (None, "%s(d_dc_du, d_q_qd, stride, nullptr, nullptr, N, g, s)" % tps("id_grad", "AlgIdGrad"))],
               [("d_qdd", "wps::wps_launch<2, true>(d_dc_du, d_q_qd, stride, d_qdd, nullptr, N, g, s)"),
-               (None, "wps::wps_launch<2, false>(d_dc_du, d_q_qd, stride, nullptr, nullptr, N, g, s)")])
+               (None, "wps::wps_launch<2, false>(d_dc_du, d_q_qd, stride, nullptr, nullptr, N, g, s)")],
+              [("d_qdd", "cps_launch<gen::ColIdGradQdd, %d>(d_dc_du, d_q_qd, stride, d_qdd, N, g, s)" % G),
+               (None, "cps_launch<gen::ColIdGrad, %d>(d_dc_du, d_q_qd, stride, nullptr, N, g, s)" % G)])
     L.append("}")
     L.append("cudaError_t launch_fd_grad(float *d_df_du, const float *d_in, int stride, const float *d_qdd,"
              " const float *d_Minv, int N, float g, cudaStream_t s) {")
@@ -364,7 +453,8 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
               [("d_qdd", "%s(d_df_du, d_in, stride, d_qdd, d_Minv, N, g, s)" % tps("fd_grad", "AlgFdGradPre")),
                (None, "%s(d_df_du, d_in, stride, nullptr, nullptr, N, g, s)" % tps("fd_grad", "AlgFdGrad"))],
               [("d_qdd", "wps::wps_launch<3, true>(d_df_du, d_in, stride, d_qdd, d_Minv, N, g, s)"),
-               (None, "wps::wps_launch<3, false>(d_df_du, d_in, stride, nullptr, nullptr, N, g, s)")])
+               (None, "wps::wps_launch<3, false>(d_df_du, d_in, stride, nullptr, nullptr, N, g, s)")],
+              [("!d_qdd", "cps_launch<gen::ColFdGrad, %d>(d_df_du, d_in, stride, nullptr, N, g, s)" % G)])
     L.append("}")
 
     kinds = "\n".join('    if (!strcmp(alg, "%s")) return "%s";' % (a, k) for a, k in plan.kind.items())

@@ -281,6 +281,40 @@ int grid_forward_dynamics_gradient(grid_data *hd, int T, float gravity, int use_
 
 }  // extern "C"
 
+extern "C" int grid_time_launches(const char *alg, float *d_out, const float *d_in, int stride, int num_timesteps,
+                                  float gravity, int reps, float *h_us) {
+    using namespace GRID_NS;
+    if (!alg || !h_us || reps <= 0 || reps > 100000) return fail_msg("bad arguments to grid_time_launches");
+    cudaStream_t s = nullptr;
+    GRID_CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
+    cudaEvent_t *ev = new cudaEvent_t[2 * (size_t)reps];
+    for (int i = 0; i < 2 * reps; i++) cudaEventCreate(&ev[i]);
+    int rc = 0;
+    for (int i = -3; i < reps && rc == 0; i++) {          // 3 warm-up launches
+        if (i >= 0) cudaEventRecord(ev[2 * i], s);
+        if (!strcmp(alg, "id")) rc = grid_inverse_dynamics_device(d_out, d_in, stride, nullptr, num_timesteps, gravity, s);
+        else if (!strcmp(alg, "minv")) rc = grid_direct_minv_device(d_out, d_in, stride, num_timesteps, s);
+        else if (!strcmp(alg, "fd")) rc = grid_forward_dynamics_device(d_out, d_in, stride, num_timesteps, gravity, s);
+        else if (!strcmp(alg, "id_grad")) rc = grid_inverse_dynamics_gradient_device(d_out, d_in, stride, nullptr, num_timesteps, gravity, s);
+        else if (!strcmp(alg, "fd_grad")) rc = grid_forward_dynamics_gradient_device(d_out, d_in, stride, nullptr, nullptr, num_timesteps, gravity, s);
+        else rc = fail_msg("unknown algorithm name");
+        if (i >= 0) cudaEventRecord(ev[2 * i + 1], s);
+    }
+    if (rc == 0) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail("grid_time_launches", e);
+        for (int i = 0; i < reps && rc == 0; i++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
+            h_us[i] = ms * 1e3f;
+        }
+    }
+    for (int i = 0; i < 2 * reps; i++) cudaEventDestroy(ev[i]);
+    delete[] ev;
+    cudaStreamDestroy(s);
+    return rc;
+}
+
 /* ---- FP32 roofline microbenchmark ------------------------------------------------------ */
 namespace GRID_NS {
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float a, float b) {

@@ -55,6 +55,8 @@ EXPORTS = {
     "grid_forward_dynamics_gradient": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int]),
     "grid_measure_fp32_tflops": (ctypes.c_double, [ctypes.c_int]),
     "grid_launch_count": (ctypes.c_longlong, []),
+    "grid_time_launches": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_float, ctypes.c_int, c_float_p]),
 }
 
 
@@ -192,6 +194,15 @@ class GridEngine:
         if v <= 0:
             raise GridError("fp32 microbenchmark failed: %s" % self.lib.grid_last_error().decode())
         return v
+
+    def time_launches(self, alg: str, out, inp, num_timesteps=None, stride=None, gravity=9.81, reps=200):
+        """Per-launch GPU durations (us) of `reps` back-to-back launches, event pairs recorded in C."""
+        stride = int(inp.shape[-1]) if stride is None else stride
+        T = int(inp.shape[0]) if num_timesteps is None else num_timesteps
+        buf = (ctypes.c_float * reps)()
+        self._check(self.lib.grid_time_launches(alg.encode(), _ptr(out), _ptr(inp), stride, T, gravity, reps, buf),
+                    "grid_time_launches")
+        return np.ctypeslib.as_array(buf).copy()
 
     def _check(self, rc: int, what: str):
         if rc != 0:

@@ -36,7 +36,8 @@ int grid_num_joints(void);              /* const int NUM_JOINTS  (GRiDCodeGenera
 const char *grid_robot_name(void);
 const char *grid_robot_hash(void);      /* hash of every robot parameter compiled in         */
 const char *grid_last_error(void);      /* message of the last failure on this thread        */
-/* "tps" (thread per state, straight-line), "wps" (warp per state) or "none" for
+/* "+"-joined kernel families available: "tps" (thread per state), "wps" (CTA per state),
+ * "cps" (lane per column, latency), or "none"; for
  * alg in {"id","minv","fd","id_grad","fd_grad"} */
 const char *grid_kernel_kind(const char *alg);
 /* live traced FP32 ops per state of the straight-line kernels (0 when not tps) */
@@ -102,6 +103,12 @@ int grid_forward_dynamics_gradient(grid_data *hd, int num_timesteps, float gravi
 /* Runs an FFMA-only microbenchmark on the current device and returns the measured FP32
  * (non-tensor) throughput in TFLOP/s (the roofline denominator); <0 on error. */
 double grid_measure_fp32_tflops(int repeats);
+/* Times `reps` back-to-back launches of one algorithm ("id","minv","fd","id_grad","fd_grad", inputs
+ * as for the matching *_device call with d_qdd = d_Minv = NULL) with one CUDA event pair per launch,
+ * recorded from C so that no interpreter time sits between the events; h_us receives the `reps`
+ * per-launch durations in microseconds.  This is how the N = 128 latency is measured. */
+int grid_time_launches(const char *alg, float *d_out, const float *d_in, int stride, int num_timesteps,
+                       float gravity, int reps, float *h_us);
 /* Number of kernels this library has launched since load (the bench's gpu_launches). */
 long long grid_launch_count(void);
 

@@ -16,7 +16,7 @@ from gridcodegenerator_b200.synthetic import make_states, pack_q_qd, pack_q_qd_u
 from oracle import rbd_numpy as O                                       # noqa: E402
 
 ALL = ("id", "minv", "fd", "id_grad", "fd_grad")
-FAMILIES = ("tps", "wps")
+FAMILIES = ("tps", "wps", "cps")
 
 
 class forced:
@@ -183,7 +183,9 @@ def test_host_path_grid_data():
     data = eng.make_data(N)
     data.h["q_qd_u"][:] = pack_q_qd_u(q, qd, u)
     df = data.forward_dynamics_gradient(N).copy()
-    assert np.array_equal(df, run_alg(eng, "fd_grad", q, qd, u))
+    # the host path pipelines the batch in chunks, and small chunks take the latency kernels:
+    # same values to rounding, not bit-identical to one big launch
+    assert relerr(df, run_alg(eng, "fd_grad", q, qd, u)) < 1e-5
     c = data.inverse_dynamics(N).copy()
     assert np.array_equal(c, run_alg(eng, "id", q, qd, u))
     data.h["qdd"][:] = qdd
@@ -191,7 +193,7 @@ def test_host_path_grid_data():
     assert np.array_equal(c2, run_alg(eng, "id", q, qd, u, qdd=qdd))
     assert np.array_equal(data.direct_minv(N).copy(), run_alg(eng, "minv", q, qd, u))
     assert np.array_equal(data.forward_dynamics(N).copy(), run_alg(eng, "fd", q, qd, u))
-    assert np.array_equal(data.inverse_dynamics_gradient(N).copy(), run_alg(eng, "id_grad", q, qd, u))
+    assert relerr(data.inverse_dynamics_gradient(N).copy(), run_alg(eng, "id_grad", q, qd, u)) < 1e-5
     with pytest.raises(GridError):
         data.forward_dynamics(N + 1)
     data.close()

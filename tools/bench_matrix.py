@@ -40,14 +40,8 @@ def main():
         for _ in range(5):
             call(out, x)
         torch.cuda.synchronize()
-        reps = 30 if N <= 4096 else 10
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        for a, b in evs:
-            a.record()
-            call(out, x)
-            b.record()
-        torch.cuda.synchronize()
-        us = np.array([a.elapsed_time(b) * 1e3 for a, b in evs])
+        reps = 100 if N <= 4096 else 20
+        us = eng.time_launches(alg, out, x, reps=reps)      # event pairs recorded in C, launches queued back to back
         p50 = float(np.median(us))
         fl = algorithmic_flops(robot)[alg]
         print(json.dumps({"spec": spec, "p50_us": p50, "min_us": float(us.min()), "evals_per_s": N / p50 * 1e6,
