@@ -101,6 +101,36 @@ def run_reference_arm(a):
     print(json.dumps(line))
 
 
+def reference_gpu_arm(robot_name, alg, N, host_in):
+    """The reference's OWN emitted CUDA (baseline/_ref/<robot>/ref_harness, built from the unmodified
+    reference by baseline/make_reference_cuh.py) timed on this GPU on the same inputs, _compute_only
+    mode.  Reported beside our numbers; absent when the harness was not built."""
+    import tempfile
+    exe = os.path.join(ROOT, "baseline", "_ref", robot_name, "ref_harness")
+    if alg != "fd_grad" or not os.path.exists(exe):
+        return {"unavailable": "baseline/_ref/%s/ref_harness not built (python baseline/make_reference_cuh.py)" % robot_name}
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        for n_states, key in ((N, "n_full"), (128, "n128")):
+            with open(os.path.join(td, "in.bin"), "wb") as f:
+                f.write(np.int32(n_states).tobytes())
+                f.write(np.ascontiguousarray(host_in[:n_states]).tobytes())
+            best = None
+            for threads in (128, 256):
+                p = subprocess.run([exe, os.path.join(td, "in.bin"), os.path.join(td, "out.bin"), str(threads), "20"],
+                                   capture_output=True, text=True, timeout=300)
+                if p.returncode == 0:
+                    r = json.loads(p.stdout.strip().splitlines()[-1])
+                    if best is None or r["p50_us"] < best["p50_us"]:
+                        best = r
+            if best:
+                out[key] = {"N": n_states, "threads": best["threads"], "p50_us": best["p50_us"],
+                            "evals_per_s": best["evals_per_s"]}
+    out["what"] = ("reference GRiDCodeGenerator's emitted forward_dynamics_gradient_compute_only kernel, nvcc sm_100a, "
+                   "best of 128/256 threads per block, CUDA events around the call")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # clocks sampler
 # ---------------------------------------------------------------------------------------------
@@ -154,6 +184,7 @@ def run_b200_arm(a):
     from gridcodegenerator_b200 import load_named_robot
     from gridcodegenerator_b200.algorithms import algorithmic_bytes, algorithmic_flops
     from gridcodegenerator_b200.runtime import get_engine
+    from gridcodegenerator_b200.sharding import max_over_ranks
     from gridcodegenerator_b200.synthetic import make_states, pack_q_qd_u, seed_for
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -227,10 +258,7 @@ def run_b200_arm(a):
     t_hi = time.perf_counter()
     gpu_launches = eng.launch_count() - launches_before
     ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = max_over_ranks(ms_total, world, device="cuda")
     ms_per_step = ms_total / a.steps
     value = world * N / (ms_per_step * 1e-3)
     clocks = sampler.stop(t_lo - 0.3, t_hi + 0.05) if rank == 0 else None
@@ -255,10 +283,7 @@ def run_b200_arm(a):
         _ = float(res[0, 0])                     # the result is in host memory when the call returns
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * e2e_steps / float(te.item())
+    e2e_value = world * N * e2e_steps / max_over_ranks(e2e_s, world, device="cuda")
     data.close()
 
     # ---- N=128 latency (second half of the BASELINE metric), 1 GPU only ----------------------
@@ -318,6 +343,8 @@ def run_b200_arm(a):
         "roofline": roofline, "latency_n128": lat,
     }
 
+    line["reference_gpu"] = reference_gpu_arm(a.robot, a.alg, N, host_in)
+
     if not a.no_cpu_baseline:
         import multiprocessing as mp
         cores = os.cpu_count() or 1
@@ -325,6 +352,17 @@ def run_b200_arm(a):
         with mp.get_context("fork").Pool(cores) as pool:
             cpu_reference_pass(a.robot, a.alg, cores * 4, cores, pool)
             v, ms1, done = cpu_reference_pass(a.robot, a.alg, sample, cores, pool)
+        try:
+            from oracle import c_oracle as C
+            qs, qds, us_, _ = (x.astype(np.float64) for x in make_states(n, N, 4242))
+            C.batch(robot, a.alg, qs[:256], qds[:256], us_[:256])
+            t0 = time.perf_counter()
+            C.batch(robot, a.alg, qs, qds, us_ if a.alg in ("fd", "fd_grad") else None, threads=cores)
+            line["cpu_baseline_c"] = {"value": N / (time.perf_counter() - t0), "unit": UNIT, "cores": cores,
+                                      "kind": "port", "sample": "full batch of %d states, oracle/rbd_oracle.c "
+                                      "(float64 C restatement, pthreads)" % N}
+        except Exception as e:                         # gcc missing on the box: the numpy baseline stands
+            line["cpu_baseline_c"] = {"unavailable": str(e)[:200]}
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "%d seeded states over %d processes, oracle/rbd_numpy.py (port of reference "
                                           "_test.py:496-520); single-core %.2f ms/eval" % (done, cores, ms1)}

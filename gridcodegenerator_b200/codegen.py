@@ -184,6 +184,96 @@ def emit_col_struct(robot: Robot, name: str, alg: str, use_qdd: bool = False) ->
     return "\n".join(L), p.op_counts()
 
 
+def emit_alg_struct_looped(robot: Robot, sname: str, alg: str, use_qdd: bool = False,
+                           pairs: bool = False) -> Tuple[str, Dict[str, int]]:
+    """Thread-per-state program with the du-columns ROLLED into a loop: the column-independent
+    part of algorithms.trace_column_program runs once, then one lane-uniform column body runs
+    2n times with 0/1 masks derived from the loop counter.  The body (~1k instructions) stays in
+    the instruction cache, which the fully unrolled program (8.5k instructions, 136 KB) does not
+    (profiles/r1b: no_instruction = 58 % of stall cycles)."""
+    from .algorithms import trace_column_program
+    n = robot.n
+    p = trace_column_program(robot, alg, use_qdd)
+    live = p.live_nodes()
+    dep = [False] * len(p.nodes)
+    for i, k in enumerate(p.nodes):
+        if k[0] == "in":
+            dep[i] = k[1].startswith("mq")
+        elif k[0] in ("sin", "cos", "rcp", "mulc", "addc"):
+            dep[i] = dep[k[1]]
+        elif k[0] in ("mul", "add"):
+            dep[i] = dep[k[1]] or dep[k[2]]
+    in0 = 3 * n if alg == "fd_grad" else 2 * n
+    in1 = n if use_qdd else 0
+    out_words = 2 * n * n
+    ind = "        "
+    pre: List[str] = []
+    body: List[str] = []
+    outs: Dict[int, list] = {}
+    for (_, idx, v) in p.outputs:
+        outs.setdefault(-1 if v.is_const else v.i, []).append((idx, v))
+    done = set()
+    for i, k in enumerate(p.nodes):
+        if live[i] and k[0] == "in" and not dep[i] and k[1] != "gravity":
+            m = _NAME_RE.match(k[1])
+            kind, idx = m.group(1), int(m.group(2))
+            word = {"q": idx, "qd": n + idx, "u": 2 * n + idx, "qdd": in0 + idx}[kind]
+            pre.append("%sconst float t%d = s_in[%d];   // %s" % (ind, i, word, k[1]))
+    pre.append(ind + "__syncwarp();")
+    for i, k in enumerate(p.nodes):
+        if not live[i]:
+            continue
+        op = k[0]
+        tgt = body if dep[i] else pre
+        pad = ind + ("    " if dep[i] else "")
+        if op == "in":
+            nm = k[1]
+            if nm == "gravity":
+                tgt.append("%sconst float t%d = gravity;" % (pad, i))
+            elif nm.startswith("mqd"):
+                tgt.append("%sconst float t%d = (col == %d) ? 1.0f : 0.0f;" % (pad, i, n + int(nm[3:])))
+            elif nm.startswith("mq"):
+                tgt.append("%sconst float t%d = (col == %d) ? 1.0f : 0.0f;" % (pad, i, int(nm[2:])))
+        elif op in ("sin", "cos"):
+            a = k[1]
+            if a not in done:
+                done.add(a)
+                si, ci = p._cse.get(("sin", a)), p._cse.get(("cos", a))
+                sn = "t%d" % si if si is not None and live[si] else "us%d" % a
+                cn = "t%d" % ci if ci is not None and live[ci] else "uc%d" % a
+                tgt.append("%sfloat %s, %s; sincosf(t%d, &%s, &%s);" % (pad, sn, cn, a, sn, cn))
+        elif op == "rcp":
+            tgt.append("%sconst float t%d = 1.0f / t%d;" % (pad, i, k[1]))
+        elif op == "mul":
+            tgt.append("%sconst float t%d = t%d * t%d;" % (pad, i, k[1], k[2]))
+        elif op == "mulc":
+            tgt.append("%sconst float t%d = t%d * %s;" % (pad, i, k[1], _flit(k[2])))
+        elif op == "add":
+            tgt.append("%sconst float t%d = t%d %s t%d;" % (pad, i, k[1], "+" if k[3] > 0 else "-", k[2]))
+        elif op == "addc":
+            tgt.append("%sconst float t%d = t%d + %s;" % (pad, i, k[1], _flit(k[2])))
+        for idx, v in outs.get(i, []):
+            body.append("%s    s_out[col * %d + %d] = %st%d;" % (ind, n, idx, "-" if v.s < 0 else "", v.i))
+    if -1 in outs:
+        raise ValueError("column program produced a constant output")
+    cnt = p.op_counts()
+    n_body = sum(1 for i, k in enumerate(p.nodes) if live[i] and dep[i] and k[0] in ("mul", "mulc", "add", "addc"))
+    cnt["loop_body_flops"] = n_body
+    cnt["flops"] = cnt["flops"] - n_body + 2 * n * n_body
+    txt = ["struct %s {" % sname,
+           "    static constexpr int IN0 = %d, IN1 = %d, IN2 = 0, OUT = %d;" % (in0, in1, out_words),
+           "    static constexpr long long TRACED_FLOPS = %d;   // %d once + %d columns x %d" % (
+               cnt["flops"], cnt["flops"] - 2 * n * n_body, 2 * n, n_body),
+           "    static __device__ __forceinline__ void eval(const float *s_in, float *s_out, const float gravity) {"]
+    txt += pre
+    txt.append(ind + "#pragma unroll 1")
+    txt.append(ind + "for (int col = 0; col < %d; ++col) {" % (2 * n))
+    txt += body
+    txt.append(ind + "}")
+    txt += ["    }", "};", ""]
+    return "\n".join(txt), cnt
+
+
 def emit_alg_struct(robot: Robot, variant: str, p: Optional[Program] = None,
                     sync_every: int = 0) -> Tuple[str, Dict[str, int]]:
     n = robot.n
@@ -300,10 +390,11 @@ class KernelPlan:
 
     def __init__(self, robot: Robot, tps_max_flops: int = 60000, tps_warps: int = 1,
                  tps_min_blocks: Optional[Dict[str, int]] = None, tps_sync_every: int = 0,
-                 wps_max_states: int = 0, cps_max_states: int = 2048):
+                 wps_max_states: int = 0, cps_max_states: int = 2048, tps_loop_columns: bool = False):
         self.robot = robot
         self.tps_warps = tps_warps
         self.tps_sync_every = tps_sync_every if tps_warps > 1 else 0
+        self.tps_loop_columns = tps_loop_columns
         alg = algorithmic_flops(robot)
         self.kind: Dict[str, str] = {}
         self.wps = wps_layout(robot)
@@ -367,6 +458,12 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
         if "tps" not in plan.kind[a]:
             continue
         for v in variants:
+            if plan.tps_loop_columns and v in ("fd_grad", "id_grad", "id_grad_qdd"):
+                txt, cnt = emit_alg_struct_looped(robot, VARIANTS[v][0], "fd_grad" if v == "fd_grad" else "id_grad",
+                                                  use_qdd=(v == "id_grad_qdd"))
+                out.append(txt)
+                stats[v] = cnt
+                continue
             txt, cnt = emit_alg_struct(robot, v, sync_every=plan.tps_sync_every)
             out.append(txt)
             stats[v] = cnt

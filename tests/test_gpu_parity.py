@@ -197,3 +197,22 @@ def test_host_path_grid_data():
     with pytest.raises(GridError):
         data.forward_dynamics(N + 1)
     data.close()
+
+
+@pytest.mark.parametrize("name,N,algs", [("iiwa14", 65536, ALL), ("hyq", 16384, ALL), ("atlas", 4096, ALL),
+                                         ("chain64", 256, ALL)])
+def test_full_batches_against_c_oracle(name, N, algs):
+    """BASELINE.json batch sizes, every state checked: the C restatement of the oracle
+    (oracle/rbd_oracle.c, pinned to the reference goldens in tests/test_oracle.py) finishes
+    these batches in seconds."""
+    from oracle import c_oracle as C
+    robot = load_named_robot(name)
+    eng = get_engine(robot)
+    q, qd, u, qdd = make_states(robot.n, N, seed_for(name) + 1)
+    q64, qd64, u64 = (x.astype(np.float64) for x in (q, qd, u))
+    for alg in algs:
+        out = run_alg(eng, alg, q, qd, u)
+        ref = C.batch(robot, alg, q64, qd64, u64 if alg in ("fd", "fd_grad") else None)
+        assert relerr(out, ref) < TOL[alg], (name, alg, relerr(out, ref))
+        per = np.abs(out - ref).max(axis=1) / np.abs(ref).max(axis=1)
+        assert per.max() < 50 * TOL[alg], (name, alg, per.max())

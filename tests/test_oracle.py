@@ -78,3 +78,20 @@ def test_oracle_matches_live_reference(name):
         ref_dc = g.test_rnea_grad(q, qd)
     assert relerr(O.fd_grad(robot, q, qd, u), ref) < 1e-10
     assert relerr(O.rnea_grad(robot, q, qd), ref_dc) < 1e-11
+
+
+@pytest.mark.parametrize("tag", ["iiwa14_damped", "hyq", "atlas", "chain64"])
+def test_c_oracle_matches_numpy_oracle_and_goldens(tag):
+    from helpers import colmajor_batch
+    from oracle import c_oracle as C
+    robot, z = load_golden(tag)
+    q, qd, u, qdd = (z[k].astype(np.float64) for k in ("q", "qd", "u", "qdd"))
+    assert relerr(C.batch(robot, "id", q, qd), z["c"]) < 1e-12
+    assert relerr(C.batch(robot, "id", q, qd, qdd), z["c_qdd"]) < 1e-12
+    assert relerr(C.batch(robot, "minv", q), colmajor_batch(z["minv_upper"])) < 1e-10
+    assert relerr(C.batch(robot, "fd", q, qd, u), z["fd_qdd"]) < 1e-9
+    assert relerr(C.batch(robot, "id_grad", q, qd), colmajor_batch(z["dc_du"])) < 1e-10
+    assert relerr(C.batch(robot, "id_grad", q, qd, qdd), colmajor_batch(z["dc_du_qdd"])) < 1e-10
+    assert relerr(C.batch(robot, "fd_grad", q, qd, u), colmajor_batch(z["df_du"])) < 1e-8
+    assert relerr(C.batch(robot, "fd_grad", q[:2], qd[:2], u[:2], threads=1),
+                  O.batch(robot, "fd_grad", q[:2], qd[:2], u[:2])) < 1e-9
