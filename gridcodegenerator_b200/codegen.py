@@ -346,11 +346,15 @@ def wps_layout(robot: Robot) -> Dict[str, object]:
     nt = 32 * max(col_warps, minv_col_warps + 2)
     # mirror of struct L in csrc/grid_wps.cuh
     Er = (5 * n + 3) // 4 * 4
-    IA = Er + 12 * n + 30 * n + n * n
+    IA = Er + 12 * n + 30 * n + 36 * n + n * n
     minv_end = IA + 36 * n + 13 * n + nslot * 6 * n
     grad_end = IA + 2 * df_words + nsave * 24 * n + 2 * n * n
     total = (max(minv_end, grad_end) + 3) // 4 * 4
+    nlevels = max(level) + 1
+    level_joints = sorted(range(n), key=lambda i: (level[i], i))
+    level_start = [sum(1 for i in range(n) if level[i] < l) for l in range(nlevels + 1)]
     return dict(N=n, NT=nt, NSLOT=nslot, NSAVE=nsave, DF_WORDS=df_words, IA_LANE0=32 * minv_col_warps,
+                NLEVELS=nlevels, level_joints=level_joints, level_start=level_start,
                 RNEA_TID=nt - 32, COL_WARPS=col_warps, level=level, nsub=nsub, slot_b=slot_b, slot_f=slot_f,
                 save=save, dfbase=dfbase, smem_bytes=4 * total)
 
@@ -365,7 +369,7 @@ def emit_wps_tables(robot: Robot, lay: Dict[str, object]) -> str:
         return "__constant__ float %s[%d] = {%s};\n" % (name, len(vals), ", ".join(_flit(float(v)) for v in vals))
 
     t = ["namespace GRID_NS { namespace gen {\n", "struct WT {\n"]
-    for k in ("N", "NT", "NSLOT", "NSAVE", "DF_WORDS", "IA_LANE0", "RNEA_TID", "COL_WARPS"):
+    for k in ("N", "NT", "NSLOT", "NSAVE", "DF_WORDS", "IA_LANE0", "RNEA_TID", "COL_WARPS", "NLEVELS"):
         t.append("    static constexpr int %s = %d;\n" % (k, lay[k]))
     t.append("};\n")
     t.append(ints("wt_parent", robot.parent))
@@ -376,9 +380,12 @@ def emit_wps_tables(robot: Robot, lay: Dict[str, object]) -> str:
     t.append(ints("wt_fslot_f", lay["slot_f"]))
     t.append(ints("wt_saveslot", lay["save"]))
     t.append(ints("wt_dfbase", lay["dfbase"]))
+    t.append(ints("wt_level_start", lay["level_start"]))
+    t.append(ints("wt_level_joints", lay["level_joints"]))
     t.append(floats("wt_E0", [x for i in range(n) for x in robot.E0[i].flatten()]))
     t.append(floats("wt_r0", [x for i in range(n) for x in robot.r0[i]]))
     t.append(floats("wt_I", [x for i in range(n) for x in robot.Imats[i].flatten()]))
+    t.append(floats("wt_I_g", [x for i in range(n) for x in robot.Imats[i].flatten()]).replace("__constant__", "__device__ const"))
     t.append(floats("wt_damping", robot.damping))
     t.append("}}  // namespace GRID_NS::gen\n")
     t.append('#include "grid_wps.cuh"\n')

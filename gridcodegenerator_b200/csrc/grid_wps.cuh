@@ -10,7 +10,8 @@
 //     by ONE lane for the whole recursion, so there are no shared-memory atomics and no
 //     barrier inside a gradient pass (the reference has 26-197); the Minv
 //     passes need one named barrier per joint;
-//   * the two RNEA sweeps run on their own warp, concurrently with the Minv passes;
+//   * the two RNEA sweeps run on their own warp (6 row-lanes per joint, a tree level at a time),
+//     the first one concurrently with the Minv passes;
 //   * X_i is kept as (E, r) (12 floats) and applied as two 3x3 products and a cross
 //     product (27 FMA) instead of a dense 6x6 (36);
 //   * F and the per-column df storage are slot-allocated at generation time from the tree
@@ -33,7 +34,8 @@ struct L {
     static constexpr int q = 0, qd = q + N, u = qd + N, qdd = u + N, c = qdd + N;
     static constexpr int Er = ((c + N + 3) / 4) * 4;          // 12 per joint, float4 aligned
     static constexpr int v = Er + 12 * N, a = v + 6 * N, f = a + 6 * N, Xa = f + 6 * N, Iv = Xa + 6 * N;
-    static constexpr int Minv = Iv + 6 * N;                    // N*N row-major [row][col], upper
+    static constexpr int Ic = Iv + 6 * N;                      // 36 per joint: link inertias, loaded once per CTA
+    static constexpr int Minv = Ic + 36 * N;                   // N*N row-major [row][col], upper
     static constexpr int IA = Minv + N * N;                    // 36 per joint, row-major
     static constexpr int U = IA + 36 * N, W = U + 6 * N, Dinv = W + 6 * N;
     static constexpr int F = Dinv + N;                         // NSLOT * 6 * N, [slot][row][col]
@@ -96,43 +98,31 @@ __device__ __forceinline__ void xtforce(const Xf &X, const float *f, float *o) {
     cross3(X.r, o + 3, t);
     o[0] += t[0]; o[1] += t[1]; o[2] += t[2];
 }
-// w x e_a  (a is warp-uniform)
+// w x e_a, branch-free (a is warp-uniform): component a is 0, (a+1)%3 gets w[(a+2)%3], (a+2)%3 gets -w[(a+1)%3]
 __device__ __forceinline__ void wxe(int a, const float *w, float *o) {
-    switch (a) {
-        case 0: o[0] = 0.f; o[1] = w[2]; o[2] = -w[1]; break;
-        case 1: o[0] = -w[2]; o[1] = 0.f; o[2] = w[0]; break;
-        default: o[0] = w[1]; o[1] = -w[0]; o[2] = 0.f; break;
-    }
+    o[0] = a == 1 ? -w[2] : (a == 2 ? w[1] : 0.f);
+    o[1] = a == 2 ? -w[0] : (a == 0 ? w[2] : 0.f);
+    o[2] = a == 0 ? -w[1] : (a == 1 ? w[0] : 0.f);
 }
 // (v x) e_k : the reference's mx0..mx5 (helpers/_spatial_algebra_helpers.py:62-147)
 __device__ __forceinline__ void mxS(int k, const float *v, float *o) {
-    if (k < 3) {
-        wxe(k, v, o);
-        wxe(k, v + 3, o + 3);
-    } else {
-        o[0] = o[1] = o[2] = 0.f;
-        wxe(k - 3, v, o + 3);
-    }
+    const int a = k < 3 ? k : k - 3;
+    float top[3], bot[3];
+    wxe(a, v, top);
+    wxe(a, v + 3, bot);
+    const bool rev = k < 3;
+    o[0] = rev ? top[0] : 0.f; o[1] = rev ? top[1] : 0.f; o[2] = rev ? top[2] : 0.f;
+    o[3] = rev ? bot[0] : top[0]; o[4] = rev ? bot[1] : top[1]; o[5] = rev ? bot[2] : top[2];
 }
 __device__ __forceinline__ float pick(const float *v, int k) {
-    switch (k) {
-        case 0: return v[0];
-        case 1: return v[1];
-        case 2: return v[2];
-        case 3: return v[3];
-        case 4: return v[4];
-        default: return v[5];
-    }
+    float r = v[0];
+#pragma unroll
+    for (int t = 1; t < 6; t++) r = (k == t) ? v[t] : r;
+    return r;
 }
 __device__ __forceinline__ void add_at(float *v, int k, float x) {
-    switch (k) {
-        case 0: v[0] += x; break;
-        case 1: v[1] += x; break;
-        case 2: v[2] += x; break;
-        case 3: v[3] += x; break;
-        case 4: v[4] += x; break;
-        default: v[5] += x; break;
-    }
+#pragma unroll
+    for (int t = 0; t < 6; t++) v[t] += (k == t) ? x : 0.f;
 }
 // v x* f : fx_times_v (helpers/_spatial_algebra_helpers.py:181-256)
 __device__ __forceinline__ void crossf(const float *v, const float *f, float *o) {
@@ -188,57 +178,115 @@ __device__ __forceinline__ void update_X(float *s, int i) {
     dst[9] = r[0]; dst[10] = r[1]; dst[11] = r[2];
 }
 
-// ---- RNEA, one thread, joints in id order (parent < child) --------------------------------
-// replaces inverse_dynamics_inner / _vaf (algorithms/_inverse_dynamics.py:33-304)
-__device__ void rnea_serial(float *s, bool use_qdd, float gravity) {
-    for (int i = 0; i < N; i++) {
-        const Xf X = load_X(s, i);
-        const int par = wt_parent[i], k = wt_S[i];
-        float v[6], a[6], xa[6], t[6], iv[6], f[6];
-        if (par < 0) {
-            const float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, gravity};
-#pragma unroll
-            for (int r = 0; r < 6; r++) v[r] = 0.f;
-            xmotion(X, g, xa);
-        } else {
-            float vp[6], ap[6];
-            load6(s + L::v + 6 * par, vp);
-            load6(s + L::a + 6 * par, ap);
-            xmotion(X, vp, v);
-            xmotion(X, ap, xa);
-        }
-        const float qdi = s[L::qd + i];
-        add_at(v, k, qdi);
-#pragma unroll
-        for (int r = 0; r < 6; r++) a[r] = xa[r];
-        if (use_qdd) add_at(a, k, s[L::qdd + i]);
-        if (par >= 0) {
-            mxS(k, v, t);
-#pragma unroll
-            for (int r = 0; r < 6; r++) a[r] = fmaf(t[r], qdi, a[r]);
-        }
-        imul(i, v, iv);
-        imul(i, a, f);
-        crossf(v, iv, t);
-#pragma unroll
-        for (int r = 0; r < 6; r++) f[r] += t[r];
-        store6(s + L::v + 6 * i, v);
-        store6(s + L::a + 6 * i, a);
-        store6(s + L::Xa + 6 * i, xa);
-        store6(s + L::Iv + 6 * i, iv);
-        store6(s + L::f + 6 * i, f);
+// ---- RNEA on one warp: 6 lanes (rows) per joint, up to 5 joints of a tree level at a time ----
+// replaces inverse_dynamics_inner / _vaf (algorithms/_inverse_dynamics.py:33-304).  Row r of X is
+// rebuilt from (E, r): rows 0-2 = [E_r | 0], rows 3-5 = [r x E_(r-3) | E_(r-3)].
+__device__ __forceinline__ void x_row(const Xf &X, int row, float *c) {
+    const int a = row < 3 ? row : row - 3;
+    const float e[3] = {X.E[3 * a], X.E[3 * a + 1], X.E[3 * a + 2]};
+    if (row < 3) {
+        c[0] = e[0]; c[1] = e[1]; c[2] = e[2]; c[3] = c[4] = c[5] = 0.f;
+    } else {
+        cross3(X.r, e, c);
+        c[3] = e[0]; c[4] = e[1]; c[5] = e[2];
     }
-    for (int i = N - 1; i >= 0; i--) {
-        const int par = wt_parent[i], k = wt_S[i];
-        float f[6];
-        load6(s + L::f + 6 * i, f);
-        s[L::c + i] = pick(f, k) + wt_damping[i] * s[L::qd + i];
-        if (par >= 0) {
-            const Xf X = load_X(s, i);
-            float t[6];
-            xtforce(X, f, t);
+}
+// column `col` of X (for X^T f): X[c][col], c = 0..5
+__device__ __forceinline__ void x_col(const Xf &X, int col, float *c) {
+    if (col < 3) {
+        c[0] = X.E[col]; c[1] = X.E[3 + col]; c[2] = X.E[6 + col];
+        float t[3];
 #pragma unroll
-            for (int r = 0; r < 6; r++) s[L::f + 6 * par + r] += t[r];
+        for (int a = 0; a < 3; a++) {
+            const float e[3] = {X.E[3 * a], X.E[3 * a + 1], X.E[3 * a + 2]};
+            cross3(X.r, e, t);
+            c[3 + a] = col == 0 ? t[0] : (col == 1 ? t[1] : t[2]);
+        }
+    } else {
+        c[0] = c[1] = c[2] = 0.f;
+        c[3] = X.E[col - 3]; c[4] = X.E[3 + col - 3]; c[5] = X.E[6 + col - 3];
+    }
+}
+
+__device__ void rnea_rows(float *s, int lane, bool use_qdd, float gravity) {
+    const int slot = lane / 6, row = lane - 6 * slot;
+    const bool lane_ok = lane < 30;
+    for (int lvl = 0; lvl < WT::NLEVELS; lvl++) {
+        const int first = wt_level_start[lvl], count = wt_level_start[lvl + 1] - first;
+        for (int base = 0; base < count; base += 5) {
+            const bool act = lane_ok && (base + slot < count);
+            const int i = act ? wt_level_joints[first + base + slot] : 0;
+            const int par = wt_parent[i], k = wt_S[i];
+            const float qdi = s[L::qd + i];
+            float vi = 0.f, xa = 0.f;
+            if (act) {
+                const Xf X = load_X(s, i);
+                float c[6];
+                x_row(X, row, c);
+                if (par < 0) {
+                    xa = c[5] * gravity;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 6; t++) {
+                        vi = fmaf(c[t], s[L::v + 6 * par + t], vi);
+                        xa = fmaf(c[t], s[L::a + 6 * par + t], xa);
+                    }
+                }
+                if (row == k) vi += qdi;
+                s[L::v + 6 * i + row] = vi;
+                s[L::Xa + 6 * i + row] = xa;
+            }
+            __syncwarp();
+            float ai = xa;
+            if (act) {
+                float v6[6], t[6];
+                load6(s + L::v + 6 * i, v6);
+                if (use_qdd && row == k) ai += s[L::qdd + i];
+                if (par >= 0) {
+                    mxS(k, v6, t);
+                    ai = fmaf(pick(t, row), qdi, ai);
+                }
+                float iv = 0.f;
+#pragma unroll
+                for (int t2 = 0; t2 < 6; t2++) iv = fmaf(s[L::Ic + 36 * i + 6 * row + t2], v6[t2], iv);
+                s[L::a + 6 * i + row] = ai;
+                s[L::Iv + 6 * i + row] = iv;
+            }
+            __syncwarp();
+            if (act) {
+                float v6[6], a6[6], iv6[6], t[6];
+                load6(s + L::v + 6 * i, v6);
+                load6(s + L::a + 6 * i, a6);
+                load6(s + L::Iv + 6 * i, iv6);
+                float f = 0.f;
+#pragma unroll
+                for (int t2 = 0; t2 < 6; t2++) f = fmaf(s[L::Ic + 36 * i + 6 * row + t2], a6[t2], f);
+                crossf(v6, iv6, t);
+                s[L::f + 6 * i + row] = f + pick(t, row);
+            }
+            __syncwarp();
+        }
+    }
+    for (int lvl = WT::NLEVELS - 1; lvl >= 0; lvl--) {
+        const int first = wt_level_start[lvl], count = wt_level_start[lvl + 1] - first;
+        for (int base = 0; base < count; base += 5) {
+            const bool act = lane_ok && (base + slot < count);
+            const int i = act ? wt_level_joints[first + base + slot] : 0;
+            const int par = wt_parent[i], k = wt_S[i];
+            if (act) {
+                float f6[6];
+                load6(s + L::f + 6 * i, f6);
+                if (row == k) s[L::c + i] = f6[row] + wt_damping[i] * s[L::qd + i];
+                if (par >= 0) {
+                    const Xf X = load_X(s, i);
+                    float c[6], acc = 0.f;
+                    x_col(X, row, c);
+#pragma unroll
+                    for (int t = 0; t < 6; t++) acc = fmaf(c[t], f6[t], acc);
+                    atomicAdd(s + L::f + 6 * par + row, acc);      // siblings of one level share a parent
+                }
+            }
+            __syncwarp();
         }
     }
 }
@@ -475,6 +523,7 @@ wps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in, int stride
     constexpr int n_in = (ALG == 0) ? N : ((ALG == 1 || (ALG == 3 && !EXTRA)) ? 3 * N : 2 * N);
     constexpr int RW = WT::RNEA_TID;                 // first thread of the RNEA warp
 
+    for (int e = tid; e < 36 * N; e += NT) s[L::Ic + e] = __ldg(wt_I_g + e);       // once per CTA
     for (long long st = blockIdx.x; st < num_states; st += gridDim.x) {
         for (int e = tid; e < n_in; e += NT) s[L::q + e] = __ldg(d_in + st * stride + e);
         if (EXTRA) {
@@ -482,23 +531,34 @@ wps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in, int stride
             if (ALG == 3)
                 for (int e = tid; e < N * N; e += NT) {
                     const int cc = e / N, rr = e - cc * N;      // global is column-major, upper triangle
-                    if (rr <= cc) s[L::Minv + rr * N + cc] = __ldg(d_Minv + st * N * N + e);
+                    if (rr <= cc) {
+                        const float m = __ldg(d_Minv + st * N * N + e);
+                        s[L::Minv + rr * N + cc] = m;
+                        s[L::Minv + cc * N + rr] = m;
+                    }
                 }
         }
         __syncthreads();
         for (int i = tid; i < N; i += NT) update_X(s, i);
         if (need_minv) {
-            for (int e = tid; e < 36 * N; e += NT) s[L::IA + e] = wt_I[e];
+            for (int e = tid; e < 36 * N; e += NT) s[L::IA + e] = s[L::Ic + e];
             for (int e = tid; e < N * N; e += NT) s[L::Minv + e] = 0.f;
         }
         __syncthreads();
         // Minv passes on warps [0, RW/32), bias forces (RNEA with qdd = 0) concurrently on the RNEA warp
         if (tid < RW) {
             if (need_minv) minv_passes(s, tid);
-        } else if (tid == RW) {
-            if (need_c0) rnea_serial(s, false, gravity);
+        } else {
+            if (need_c0) rnea_rows(s, tid - RW, false, gravity);
         }
         __syncthreads();
+        if (need_minv && ALG != 0) {                 // mirror the upper triangle: later reads are plain loads
+            for (int e = tid; e < N * N; e += NT) {
+                const int rr = e / N, cc = e - rr * N;
+                if (rr > cc) s[L::Minv + e] = s[L::Minv + cc * N + rr];
+            }
+            __syncthreads();
+        }
         if (ALG == 0) {
             float *o = d_out + st * N * N;
             for (int e = tid; e < N * N; e += NT) {
@@ -509,7 +569,7 @@ wps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in, int stride
         if (need_c0) {        // forward_dynamics_finish (algorithms/_forward_dynamics.py:21-49)
             for (int r = tid; r < N; r += NT) {
                 float acc = 0.f;
-                for (int k = 0; k < N; k++) acc = fmaf(minv_sym(s, r, k), s[L::u + k] - s[L::c + k], acc);
+                for (int k = 0; k < N; k++) acc = fmaf(s[L::Minv + r * N + k], s[L::u + k] - s[L::c + k], acc);
                 s[L::qdd + r] = acc;
             }
             __syncthreads();
@@ -517,9 +577,9 @@ wps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in, int stride
                 for (int r = tid; r < N; r += NT) d_out[st * N + r] = s[L::qdd + r];
         }
         if (ALG >= 2) {
-            if (tid == RW) rnea_serial(s, ALG == 3 ? true : EXTRA, gravity);
+            if (tid >= RW) rnea_rows(s, tid - RW, ALG == 3 ? true : EXTRA, gravity);
             else
-                for (int e = (tid > RW ? tid - 1 : tid); e < 2 * N * N; e += NT - 1) s[L::dc + e] = 0.f;
+                for (int e = tid; e < 2 * N * N; e += RW) s[L::dc + e] = 0.f;
             __syncthreads();
             if (tid < WT::COL_WARPS * 32)            // whole warps: grad_column votes with a full mask
                 grad_column(s, tid < 2 * N ? tid : 2 * N - 1, tid < 2 * N);
@@ -537,7 +597,7 @@ wps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in, int stride
                     for (int r = 0; r < N; r++) {
                         float acc = 0.f;
 #pragma unroll
-                        for (int k = 0; k < N; k++) acc = fmaf(minv_sym(s, r, k), dcol[k], acc);
+                        for (int k = 0; k < N; k++) acc = fmaf(s[L::Minv + r * N + k], dcol[k], acc);
                         s[L::dc + col * N + r] = -acc;
                     }
                 }
