@@ -27,7 +27,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .ir import Program, V, cross3, dot, matvec, vadd, vsub, vscale, zeros
+from .ir import Program, V, V2, cross3, dot, matvec, vadd, vsub, vscale, zeros
 from .robot import Robot
 
 
@@ -511,6 +511,143 @@ def trace_column_program(robot: Robot, alg: str, use_qdd: bool = False) -> Progr
     return p
 
 
+class ColumnSource:
+    """Where a gradient column reads the per-joint state data (v, I v, mxS(X a_parent), mxS(f)) from.
+    Default: the values traced by rnea() themselves (they stay live in registers from the RNEA to the
+    last column that needs them).  With `park` set, the named groups are parked in per-lane shared
+    memory after the RNEA and RE-LOADED by every column, which cuts ~100-150 long-lived registers so
+    that more warps fit on an SM (the straight-line kernels are bound by per-warp instruction
+    supply, profiles/r1b)."""
+
+    def __init__(self, sr: "SymRobot", R: "RneaResult", park: Sequence[str] = ()):
+        p, robot, n = sr.p, sr.robot, sr.n
+        self.sr, self.R, self.p = sr, R, p
+        self.park = set(park)
+        self.mXa = [cross_motion_axis(p, robot.S_ind[i], R.Xa[i]) for i in range(n)]
+        self.mf = [cross_motion_axis(p, robot.S_ind[i], R.f[i]) for i in range(n)]
+        self.h = {}
+        for name, vals in (("v", R.v), ("Iv", R.Iv), ("mXa", self.mXa), ("mf", self.mf)):
+            if name in self.park:
+                self.h[name] = [[p.park(x) for x in vals[i]] for i in range(n)]
+        self.cache = {}
+
+    def begin_column(self):
+        self.cache = {}
+
+    def _get(self, name, i, direct):
+        if name not in self.park:
+            return direct
+        key = (name, i)
+        if key not in self.cache:
+            self.cache[key] = [self.p.unpark(h) for h in self.h[name][i]]
+        return self.cache[key]
+
+    def v(self, i):
+        return self._get("v", i, self.R.v[i])
+
+    def Iv(self, i):
+        if "Iv" in self.park or "v" not in self.park:
+            return self._get("Iv", i, self.R.Iv[i])
+        key = ("Iv", i)                      # recompute I v from the re-loaded v
+        if key not in self.cache:
+            self.cache[key] = self.sr.I_mul(i, self.v(i))
+        return self.cache[key]
+
+    def mxs_Xa(self, i):
+        return self._get("mXa", i, self.mXa[i])
+
+    def mxs_f(self, i):
+        return self._get("mf", i, self.mf[i])
+
+
+# ---- paired gradient columns: (d/dq_j, d/dqd_j) travel together as float2 ------------------------
+def rnea_grad_columns_paired(sr: SymRobot, qd: Sequence[V], R: RneaResult, src: Optional[ColumnSource] = None):
+    """Same recursion as rnea_grad_columns, with the two columns of joint j carried as ONE pair
+    value per component (ir.V2): every operation on them multiplies by the same state-level
+    scalar, which is exactly what the packed FFMA2/FMUL2/FADD2 instructions of sm_100 offer."""
+    p, robot, n = sr.p, sr.robot, sr.n
+    src = src or ColumnSource(sr, R)
+    for j in range(n):
+        src.begin_column()
+        sub = robot.get_subtree_by_id(j)
+        dv, da, df = {}, {}, {}
+        for i in sub:
+            k = robot.S_ind[i]
+            vi = src.v(i)
+            if i == j:
+                mv = cross_motion_axis(p, k, vi)
+                e = zeros(p, 6)
+                e[k] = p.const(1.0)
+                da_q = vadd(cross_motion_axis(p, k, mv, qd[i]), src.mxs_Xa(i))
+                dv[i] = [p.pack(mv[r], e[r]) for r in range(6)]
+                da[i] = [p.pack(da_q[r], mv[r]) for r in range(6)]
+            else:
+                par = robot.parent[i]
+                dv[i] = sr.X_motion(i, dv[par])
+                da[i] = vadd(sr.X_motion(i, da[par]), cross_motion_axis(p, k, dv[i], qd[i]))
+            df[i] = vadd(vadd(sr.I_mul(i, da[i]), cross_force(dv[i], src.Iv(i))),
+                         cross_force(vi, sr.I_mul(i, dv[i])))
+        cols = {}
+        for i in reversed(sub):
+            cols[i] = df[i][robot.S_ind[i]]
+            if i != j:
+                par = robot.parent[i]
+                df[par] = vadd(df[par], sr.XT_force(i, df[i]))
+        mf = src.mxs_f(j)
+        up = [df[j][r] - p.pack(mf[r], 0.0) for r in range(6)]
+        i = j
+        while robot.parent[i] >= 0:
+            up = sr.XT_force(i, up)
+            i = robot.parent[i]
+            cols[i] = up[robot.S_ind[i]]
+        cols[j] = cols[j] + p.pack(0.0, robot.damping[j])
+        yield j, cols
+
+
+def trace_id_grad_paired(robot: Robot, use_qdd: bool = False, park: Sequence[str] = ()) -> Program:
+    p = Program()
+    n = robot.n
+    q, qd = _inputs(p, n, ("q", "qd"))
+    qdd = _inputs(p, n, ("qdd",))[0] if use_qdd else None
+    g = p.inp("gravity")
+    sr = SymRobot(p, robot, q)
+    R = rnea(sr, qd, qdd, g)
+    for j, cols in rnea_grad_columns_paired(sr, qd, R, ColumnSource(sr, R, park)):
+        for i in range(n):
+            c = p.lift2(cols.get(i, 0.0))
+            p.output("dc_du", n * j + i, c.x())
+            p.output("dc_du", n * n + n * j + i, c.y())
+    return p
+
+
+def trace_fd_grad_paired(robot: Robot, use_qdd_minv: bool = False, park: Sequence[str] = ()) -> Program:
+    p = Program()
+    n = robot.n
+    q, qd = _inputs(p, n, ("q", "qd"))
+    g = p.inp("gravity")
+    sr = SymRobot(p, robot, q)
+    if use_qdd_minv:
+        qdd = _inputs(p, n, ("qdd",))[0]
+        Mi = {(r, c): p.inp("Minv%d" % (c * n + r)) for r in range(n) for c in range(r, n)}
+    else:
+        (u,) = _inputs(p, n, ("u",))
+        R0 = rnea(sr, qd, None, g)
+        Mi = minv(sr)
+        umc = [u[i] - R0.c[i] for i in range(n)]
+        qdd = [dot([minv_get(Mi, i, j) for j in range(n)], umc) for i in range(n)]
+    R = rnea(sr, qd, qdd, g)
+    src = ColumnSource(sr, R, park)
+    Mh = {k: p.park(v) for k, v in Mi.items()} if "Minv" in park else None
+    for j, cols in rnea_grad_columns_paired(sr, qd, R, src):
+        rows = sorted(cols)
+        Mj = {k: p.unpark(h) for k, h in Mh.items()} if Mh else Mi
+        for i in range(n):
+            acc = p.lift2(-dot([minv_get(Mj, i, r) for r in rows], [cols[r] for r in rows]))
+            p.output("df_du", n * j + i, acc.x())
+            p.output("df_du", n * n + n * j + i, acc.y())
+    return p
+
+
 TRACERS = {
     "id": lambda robot: trace_id(robot, False),
     "id_qdd": lambda robot: trace_id(robot, True),
@@ -520,6 +657,14 @@ TRACERS = {
     "id_grad_qdd": lambda robot: trace_id_grad(robot, True),
     "fd_grad": lambda robot: trace_fd_grad(robot, False),
     "fd_grad_qdd_minv": lambda robot: trace_fd_grad(robot, True),
+}
+
+# packed (float2) variants of the gradient programs
+PAIRED_TRACERS = {
+    "id_grad": lambda robot: trace_id_grad_paired(robot, False),
+    "id_grad_qdd": lambda robot: trace_id_grad_paired(robot, True),
+    "fd_grad": lambda robot: trace_fd_grad_paired(robot, False),
+    "fd_grad_qdd_minv": lambda robot: trace_fd_grad_paired(robot, True),
 }
 
 

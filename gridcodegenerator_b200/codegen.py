@@ -45,7 +45,7 @@ def _flit(x: float) -> str:
 
 
 def emit_eval(p: Program, n: int, in0_words: int, in1_words: int, out_name: str, out_words: int,
-              indent: str = "        ", sync_every: int = 0) -> Tuple[List[str], Dict[str, int]]:
+              indent: str = "        ", sync_every: int = 0, col_flush: bool = False) -> Tuple[List[str], Dict[str, int]]:
     """Prints the live part of ``p`` as straight-line CUDA.  Stores are emitted at the
     point in the trace where the algorithm produced them, so finished output columns do
     not occupy registers."""
@@ -85,8 +85,61 @@ def emit_eval(p: Program, n: int, in0_words: int, in1_words: int, out_name: str,
         if live[i] and k[0] == "in" and k[1] != "gravity":
             lines.append("%sconst float t%d = s_in[%d];   // %s" % (indent, i, word_of(k[1]), k[1]))
     lines.append(indent + "__syncwarp();")
-    for idx, v in outs_by_pos.get(-1, []):
-        body.append("%ss_out[%d] = %s;" % (indent, idx, _flit(v.c)))
+    parks = getattr(p, "parks", {})
+
+    def store_stmt(idx, expr):
+        if not col_flush:
+            return "%ss_out[%d] = %s;" % (indent, idx, expr)
+        sgrp, rem = divmod(idx, n * n)
+        return "%ss_col[%d] = %s;" % (indent, sgrp * n + rem % n, expr)
+
+    # column-pair groups: (idx % n*n) // n ; flushed after their last traced output
+    const_by_group: Dict[int, list] = {}
+    last_pos: Dict[int, int] = {}
+    if col_flush:
+        for (_, idx, v) in p.outputs:
+            j = (idx % (n * n)) // n
+            if v.is_const:
+                const_by_group.setdefault(j, []).append((idx, v))
+            else:
+                last_pos[j] = max(last_pos.get(j, -1), v.i)
+        flush_at: Dict[int, list] = {}
+        for j, pos in last_pos.items():
+            flush_at.setdefault(pos, []).append(j)
+    else:
+        for idx, v in outs_by_pos.get(-1, []):
+            body.append(store_stmt(idx, _flit(v.c)))
+    # packed-pair peephole: a pair product with a single use that is a pair addition becomes FFMA2
+    uses = [0] * len(p.nodes)
+    for i in range(len(p.nodes)):
+        if live[i]:
+            for o in p.operands(i):
+                uses[o] += 1
+    for (_, _, v) in p.outputs:
+        if not v.is_const:
+            uses[v.i] += 1
+    fused_into: Dict[int, int] = {}          # product node -> the addition that absorbs it
+    for i, k in enumerate(p.nodes):
+        if live[i] and k[0] == "add2":
+            for cand in (k[2], k[1]):
+                kc = p.nodes[cand]
+                if kc[0] in ("mul2", "mul2c") and uses[cand] == 1 and cand not in fused_into:
+                    fused_into[cand] = i
+                    break
+
+    def pair_scalar(kc, negate):
+        """Second operand of a pair product as a broadcast float2 expression."""
+        if kc[0] == "mul2":
+            return "make_float2(%st%d, %st%d)" % (("-" if negate else ""), kc[2], ("-" if negate else ""), kc[2])
+        c = _flit(-kc[2] if negate else kc[2])
+        return "make_float2(%s, %s)" % (c, c)
+
+    def neg_pair(idx, negate):
+        return "make_float2(-p%d.x, -p%d.y)" % (idx, idx) if negate else "p%d" % idx
+
+    def half_expr(h):
+        return _flit(h[1]) if h[0] == "c" else "%st%d" % ("-" if h[2] < 0 else "", h[1])
+
     emitted = 0
     for i, k in enumerate(p.nodes):
         if not live[i]:
@@ -116,8 +169,39 @@ def emit_eval(p: Program, n: int, in0_words: int, in1_words: int, out_name: str,
             body.append("%sconst float t%d = t%d %s t%d;" % (indent, i, k[1], "+" if k[3] > 0 else "-", k[2]))
         elif op == "addc":
             body.append("%sconst float t%d = t%d + %s;" % (indent, i, k[1], _flit(k[2])))
+        elif op == "pk":
+            body.append("%sconst float2 p%d = make_float2(%s, %s);" % (indent, i, half_expr(k[1]), half_expr(k[2])))
+        elif op == "half":
+            body.append("%sconst float t%d = p%d.%s;" % (indent, i, k[1], "xy"[k[2]]))
+        elif op in ("mul2", "mul2c"):
+            if i not in fused_into:
+                body.append("%sconst float2 p%d = __fmul2_rn(p%d, %s);" % (indent, i, k[1], pair_scalar(k, False)))
+        elif op == "add2":
+            lo, hi, rel = k[1], k[2], k[3]
+            if fused_into.get(hi) == i:          # lo + rel * (P * s)
+                kc = p.nodes[hi]
+                body.append("%sconst float2 p%d = __ffma2_rn(p%d, %s, p%d);" % (indent, i, kc[1], pair_scalar(kc, rel < 0), lo))
+            elif fused_into.get(lo) == i:        # (P * s) + rel * hi
+                kc = p.nodes[lo]
+                body.append("%sconst float2 p%d = __ffma2_rn(p%d, %s, %s);" % (indent, i, kc[1], pair_scalar(kc, False),
+                                                                            neg_pair(hi, rel < 0)))
+            else:
+                body.append("%sconst float2 p%d = __fadd2_rn(p%d, %s);" % (indent, i, lo, neg_pair(hi, rel < 0)))
+        elif op == "add2k":
+            body.append("%sconst float2 p%d = __fadd2_rn(p%d, make_float2(%s, %s));" % (indent, i, k[1], _flit(k[2]), _flit(k[3])))
+        elif op == "ld":
+            body.append("%sconst float t%d = s_park[%d];" % (indent, i, 32 * k[1]))
+        if i in parks:
+            body.append("%ss_park[%d] = t%d;" % (indent, 32 * parks[i], i))
         for idx, v in outs_by_pos.get(i, []):
-            body.append("%ss_out[%d] = %st%d;" % (indent, idx, "-" if v.s < 0 else "", v.i))
+            body.append(store_stmt(idx, "%st%d" % ("-" if v.s < 0 else "", v.i)))
+        if col_flush and i in flush_at:
+            for j in sorted(flush_at[i]):
+                for idx, v in const_by_group.get(j, []):
+                    body.append(store_stmt(idx, _flit(v.c)))
+                body.append("%s__syncwarp();" % indent)
+                body.append("%sflush_colpair<%d>(g_tile, s_warp, %d, cnt, lane);" % (indent, n, j))
+                body.append("%s__syncwarp();" % indent)
     return lines + body, p.op_counts()
 
 
@@ -392,16 +476,45 @@ def emit_wps_tables(robot: Robot, lay: Dict[str, object]) -> str:
     return "".join(t)
 
 
+def emit_alg_struct_v2(robot: Robot, variant: str, park=()) -> Tuple[str, Dict[str, int]]:
+    """Gradient program for csrc/grid_tps.cuh tps2_kernel: paired (float2) columns, per-column flush,
+    optional parking of per-joint data in lane-private shared memory."""
+    from .algorithms import trace_fd_grad_paired, trace_id_grad_paired
+    n = robot.n
+    sname, m0, m1, m2, out_name, out_fn = VARIANTS[variant]
+    in0, in1, in2, out = m0 * n, m1 * n, m2 * n * n, out_fn(n)
+    if variant.startswith("fd_grad"):
+        p = trace_fd_grad_paired(robot, variant == "fd_grad_qdd_minv", park)
+    else:
+        p = trace_id_grad_paired(robot, variant == "id_grad_qdd", [x for x in park if x != "Minv"])
+    body, cnt = emit_eval(p, n, in0, in1, out_name, out, col_flush=True)
+    slots = len(getattr(p, "parks", {}))
+    cnt["park_slots"] = slots
+    txt = ["struct %s {" % sname,
+           "    static constexpr int IN0 = %d, IN1 = %d, IN2 = %d, OUT = %d, NJ = %d, PARK_SLOTS = %d;" % (
+               in0, in1, in2, out, n, slots),
+           "    static constexpr long long TRACED_FLOPS = %d;   // %d mul + %d add per state, %d packed instructions" % (
+               cnt["flops"], cnt["mul"], cnt["add"], cnt.get("packed", 0)),
+           "    static __device__ __forceinline__ void eval(const float *s_in, float *s_col, float *s_park,"
+           " float *__restrict__ g_tile, const int cnt, const int lane, const float *s_warp, const float gravity) {"]
+    txt += body
+    txt += ["    }", "};", ""]
+    return "\n".join(txt), cnt
+
+
 class KernelPlan:
     """Which kernel family serves each algorithm of a robot, and its launch shape."""
 
     def __init__(self, robot: Robot, tps_max_flops: int = 60000, tps_warps: int = 1,
                  tps_min_blocks: Optional[Dict[str, int]] = None, tps_sync_every: int = 0,
-                 wps_max_states: int = 0, cps_max_states: int = 2048, tps_loop_columns: bool = False):
+                 wps_max_states: int = 0, cps_max_states: int = 2048, tps_loop_columns: bool = False,
+                 tps_pairs: bool = False, tps_v2_park=None):
         self.robot = robot
         self.tps_warps = tps_warps
         self.tps_sync_every = tps_sync_every if tps_warps > 1 else 0
         self.tps_loop_columns = tps_loop_columns
+        self.tps_pairs = tps_pairs
+        self.tps_v2_park = tps_v2_park          # None = variant 1; tuple of parked groups = variant 2
         alg = algorithmic_flops(robot)
         self.kind: Dict[str, str] = {}
         self.wps = wps_layout(robot)
@@ -471,7 +584,17 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
                 out.append(txt)
                 stats[v] = cnt
                 continue
-            txt, cnt = emit_alg_struct(robot, v, sync_every=plan.tps_sync_every)
+            if plan.tps_v2_park is not None and v in ("fd_grad", "fd_grad_qdd_minv", "id_grad", "id_grad_qdd"):
+                txt, cnt = emit_alg_struct_v2(robot, v, plan.tps_v2_park)
+                out.append(txt)
+                stats[v] = cnt
+                continue
+            prog = None
+            if plan.tps_pairs:
+                from .algorithms import PAIRED_TRACERS
+                if v in PAIRED_TRACERS:
+                    prog = PAIRED_TRACERS[v](robot)
+            txt, cnt = emit_alg_struct(robot, v, p=prog, sync_every=plan.tps_sync_every)
             out.append(txt)
             stats[v] = cnt
     has_cps = any("cps" in k for k in plan.kind.values())
@@ -492,6 +615,8 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
         out.append(emit_wps_tables(robot, plan.wps))
 
     def tps(a, struct):
+        if plan.tps_v2_park is not None and a in ("id_grad", "fd_grad"):
+            return "tps2_launch<%s, %d, %d>" % (struct, W, plan.min_blocks[a])
         return "tps_launch<%s, %d, %d>" % (struct, W, plan.min_blocks[a])
 
     def body(a, tps_call, wps_call, cps_call=()):

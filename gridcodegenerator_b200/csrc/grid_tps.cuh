@@ -92,6 +92,78 @@ tps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int strid
     tps_body<A>(d_out, d_in0, stride0, d_in1, d_in2, num_states, gravity);
 }
 
+// ---- variant 2: per-column output flush + parked per-state data ------------------------------
+// The gradient programs can park long-lived per-joint values in a lane-private shared-memory
+// column (slot-major, conflict-free) and re-load them in every du-column, and they flush each
+// finished column pair to global memory instead of staging the whole 2n*n output tile.  Both cut
+// shared memory and registers per warp so that more warps are resident per scheduler.
+template <int NJ>
+__device__ __forceinline__ void flush_colpair(float *__restrict__ g_tile, const float *s_warp, int j, int cnt, int lane) {
+    constexpr int W = 2 * NJ, PAD = W | 1, OUT = 2 * NJ * NJ;
+    for (int e = lane; e < cnt * W; e += 32) {
+        const int s = e / W, c = e - s * W;
+        g_tile[s * OUT + (c < NJ ? NJ * j + c : NJ * NJ + NJ * j + c - NJ)] = s_warp[s * PAD + c];
+    }
+}
+
+template <class A>
+struct Tps2Shape {
+    static constexpr int IN = A::IN0 + A::IN1 + A::IN2;
+    static constexpr int IN_PAD = odd_pad(IN);
+    static constexpr int COL_PAD = odd_pad(2 * A::NJ);
+    static constexpr int STAGE_WORDS = 32 * cmax(IN_PAD, COL_PAD);
+    static constexpr int WARP_WORDS = STAGE_WORDS + 32 * A::PARK_SLOTS;
+};
+
+template <class A, int WARPS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(32 * WARPS, MIN_BLOCKS)
+tps2_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0,
+            const float *__restrict__ d_in1, const float *__restrict__ d_in2, int num_states, float gravity) {
+    using S = Tps2Shape<A>;
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *sw = smem + warp * S::WARP_WORDS;
+    float *sp = sw + S::STAGE_WORDS + lane;
+    const int ntiles = (num_states + 31) >> 5;
+    for (int tile = blockIdx.x * WARPS + warp; tile < ntiles; tile += gridDim.x * WARPS) {
+        const long long first = (long long)tile * 32;
+        const int cnt = min(32, num_states - (int)first);
+        tile_load<A::IN0, S::IN_PAD>(sw, 0, d_in0, first, stride0, cnt, lane);
+        tile_load<A::IN1, S::IN_PAD>(sw, A::IN0, d_in1, first, A::IN1, cnt, lane);
+        tile_load<A::IN2, S::IN_PAD>(sw, A::IN0 + A::IN1, d_in2, first, A::IN2, cnt, lane);
+        __syncwarp();
+        const int src = min(lane, cnt - 1);
+        A::eval(sw + src * S::IN_PAD, sw + lane * S::COL_PAD, sp, d_out + first * A::OUT, cnt, lane, sw, gravity);
+        __syncwarp();
+    }
+}
+
+template <class A, int WARPS, int MIN_BLOCKS>
+cudaError_t tps2_launch(float *d_out, const float *d_in0, int stride0, const float *d_in1, const float *d_in2,
+                        int num_states, float gravity, cudaStream_t stream) {
+    using S = Tps2Shape<A>;
+    if (num_states <= 0) return cudaSuccess;
+    auto kern = tps2_kernel<A, WARPS, MIN_BLOCKS>;
+    constexpr size_t smem_bytes = sizeof(float) * S::WARP_WORDS * WARPS;
+    static int cap = 0;
+    if (cap == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * WARPS, smem_bytes);
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        cap = sms * per_sm;
+    }
+    const int ntiles = (num_states + 31) / 32;
+    int blocks = (ntiles + WARPS - 1) / WARPS;
+    if (blocks > cap) blocks = cap;
+    kern<<<blocks, 32 * WARPS, smem_bytes, stream>>>(d_out, d_in0, stride0, d_in1, d_in2, num_states, gravity);
+    return cudaGetLastError();
+}
+
 template <class A, int WARPS, int MIN_BLOCKS>
 cudaError_t tps_launch(float *d_out, const float *d_in0, int stride0, const float *d_in1, const float *d_in2,
                        int num_states, float gravity, cudaStream_t stream) {

@@ -45,23 +45,80 @@ class V:
         return V(self.p, i=self.i, s=-self.s)
 
     def __add__(self, o):
+        if isinstance(o, V2):
+            return o + self
         return self.p.add(self, self.p.lift(o))
 
     __radd__ = __add__
 
     def __sub__(self, o):
+        if isinstance(o, V2):
+            return (-o) + self
         return self.p.add(self, -self.p.lift(o))
 
     def __rsub__(self, o):
         return self.p.add(self.p.lift(o), -self)
 
     def __mul__(self, o):
+        if isinstance(o, V2):
+            return o * self
         return self.p.mul(self, self.p.lift(o))
 
     __rmul__ = __mul__
 
     def __repr__(self):
         return "V(c=%r)" % self.c if self.is_const else "V(%s t%d)" % ("+" if self.s > 0 else "-", self.i)
+
+
+class V2:
+    """A PAIR of values that always undergo the same operation with the same scalar - the d/dq_j
+    and d/dqd_j columns of the gradients.  Emitted as float2 and computed with the sm_100 packed
+    FP32 instructions (FFMA2 / FMUL2 / FADD2: one issue slot, two lanes), whose second operand
+    may be a scalar register broadcast to both halves.  Either a constant pair c = (cx, cy) or a
+    signed reference to a pair node."""
+    __slots__ = ("p", "c", "i", "s")
+
+    def __init__(self, p: "Program", c=None, i: int = -1, s: int = 1):
+        self.p, self.c, self.i, self.s = p, c, i, s
+
+    @property
+    def is_const(self) -> bool:
+        return self.c is not None
+
+    def is_zero(self) -> bool:
+        return self.c is not None and self.c[0] == 0.0 and self.c[1] == 0.0
+
+    def __neg__(self):
+        if self.is_const:
+            return V2(self.p, c=(-self.c[0], -self.c[1]))
+        return V2(self.p, i=self.i, s=-self.s)
+
+    def __add__(self, o):
+        return self.p.add2(self, self.p.lift2(o))
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self.p.add2(self, -self.p.lift2(o))
+
+    def __rsub__(self, o):
+        return self.p.add2(self.p.lift2(o), -self)
+
+    def __mul__(self, o):
+        if isinstance(o, V2):
+            raise TypeError("pair x pair products do not occur in the column recursions")
+        return self.p.mul2(self, self.p.lift(o))
+
+    __rmul__ = __mul__
+
+    def x(self) -> V:
+        return self.p.half(self, 0)
+
+    def y(self) -> V:
+        return self.p.half(self, 1)
+
+    def __repr__(self):
+        return "V2(c=%r)" % (self.c,) if self.is_const else "V2(%s p%d)" % ("+" if self.s > 0 else "-", self.i)
 
 
 class Program:
@@ -155,6 +212,86 @@ class Program:
         # lo.s * (t_lo + (lo.s*hi.s) * t_hi)
         return V(self, i=self._node(("add", lo.i, hi.i, lo.s * hi.s)), s=lo.s)
 
+    # pairs ----------------------------------------------------------------------------
+    def lift2(self, x) -> "V2":
+        if isinstance(x, V2):
+            return x
+        if isinstance(x, V):
+            if x.is_const:
+                return V2(self, c=(x.c, x.c))
+            return self.pack(x, x)
+        return V2(self, c=(float(x), float(x)))
+
+    def pack(self, a, b) -> "V2":
+        """Pair from two scalars (x = a, y = b)."""
+        a, b = self.lift(a), self.lift(b)
+        if a.is_const and b.is_const:
+            return V2(self, c=(a.c, b.c))
+        ha = ("c", a.c) if a.is_const else ("n", a.i, a.s)
+        hb = ("c", b.c) if b.is_const else ("n", b.i, b.s)
+        return V2(self, i=self._node(("pk", ha, hb)))
+
+    def half(self, P: "V2", which: int) -> V:
+        if P.is_const:
+            return self.const(P.c[which])
+        k = self.nodes[P.i]
+        if k[0] == "pk":                       # see through a fresh pack
+            h = k[1 + which]
+            v = self.const(h[1]) if h[0] == "c" else V(self, i=h[1], s=h[2])
+            return v if P.s > 0 else -v
+        return V(self, i=self._node(("half", P.i, which)), s=P.s)
+
+    def mul2(self, P: "V2", sc: V) -> "V2":
+        if P.is_const:
+            if sc.is_const:
+                return V2(self, c=(P.c[0] * sc.c, P.c[1] * sc.c))
+            return self.pack(sc * P.c[0], sc * P.c[1])
+        if sc.is_const:
+            c = sc.c
+            if c == 0.0:
+                return V2(self, c=(0.0, 0.0))
+            if c == 1.0:
+                return P
+            if c == -1.0:
+                return -P
+            return V2(self, i=self._node(("mul2c", P.i, abs(c))), s=P.s * (1 if c > 0 else -1))
+        return V2(self, i=self._node(("mul2", P.i, sc.i)), s=P.s * sc.s)
+
+    def add2(self, P: "V2", Q: "V2") -> "V2":
+        if P.is_const and Q.is_const:
+            return V2(self, c=(P.c[0] + Q.c[0], P.c[1] + Q.c[1]))
+        if P.is_const:
+            P, Q = Q, P
+        if Q.is_const:
+            if Q.is_zero():
+                return P
+            return V2(self, i=self._node(("add2k", P.i, P.s * Q.c[0], P.s * Q.c[1])), s=P.s)
+        if P.i == Q.i:
+            if P.s == Q.s:
+                return self.mul2(P, self.const(2.0))
+            return V2(self, c=(0.0, 0.0))
+        lo, hi = (P, Q) if P.i < Q.i else (Q, P)
+        return V2(self, i=self._node(("add2", lo.i, hi.i, lo.s * hi.s)), s=lo.s)
+
+    # explicit parking of long-lived values in per-lane shared memory ------------------------
+    def park(self, v: V):
+        """Stores v in a private shared-memory slot right after it is computed; returns a handle.
+        Constants are not parked (the handle is the constant)."""
+        if v.is_const:
+            return ("c", v.c)
+        if not hasattr(self, "parks"):
+            self.parks: Dict[int, int] = {}
+        slot = self.parks.setdefault(v.i, len(self.parks))
+        return ("s", slot, v.i, v.s)
+
+    def unpark(self, handle) -> V:
+        """A FRESH load of a parked value (never CSE'd with earlier loads): the register copy
+        lives only as long as its uses, instead of from the producer to the last column."""
+        if handle[0] == "c":
+            return self.const(handle[1])
+        self._ld_uid = getattr(self, "_ld_uid", 0) + 1
+        return V(self, i=self._node(("ld", handle[1], handle[2], self._ld_uid)), s=handle[3])
+
     def output(self, name: str, index: int, v) -> None:
         self.outputs.append((name, int(index), self.lift(v)))
 
@@ -167,13 +304,21 @@ class Program:
             if live[i]:
                 continue
             live[i] = True
-            k = self.nodes[i]
-            if k[0] in ("sin", "cos", "rcp", "mulc", "addc"):
-                stack.append(k[1])
-            elif k[0] in ("mul", "add"):
-                stack.append(k[1])
-                stack.append(k[2])
+            stack.extend(self.operands(i))
         return live
+
+    def operands(self, i: int) -> List[int]:
+        k = self.nodes[i]
+        op = k[0]
+        if op in ("sin", "cos", "rcp", "mulc", "addc", "mul2c", "add2k", "half"):
+            return [k[1]]
+        if op in ("mul", "add", "mul2", "add2"):
+            return [k[1], k[2]]
+        if op == "pk":
+            return [h[1] for h in (k[1], k[2]) if h[0] == "n"]
+        if op == "ld":
+            return [k[2]]
+        return []
 
     def op_counts(self) -> Dict[str, int]:
         """Counts of live operations; 'flops' counts mul/add as 1 each (an FMA the
@@ -187,6 +332,14 @@ class Program:
                 cnt["mul"] += 1
             elif k[0] in ("add", "addc"):
                 cnt["add"] += 1
+            elif k[0] in ("mul2", "mul2c"):
+                cnt["mul"] += 2
+                cnt["packed"] = cnt.get("packed", 0) + 1
+            elif k[0] in ("add2", "add2k"):
+                cnt["add"] += 2
+                cnt["packed"] = cnt.get("packed", 0) + 1
+            elif k[0] in ("pk", "half"):
+                pass
             elif k[0] in ("sin", "cos"):
                 cnt["sincos"] += 1
             elif k[0] == "rcp":
@@ -225,6 +378,24 @@ class Program:
                 vals[i] = vals[k[1]] + vals[k[2]] if k[3] > 0 else vals[k[1]] - vals[k[2]]
             elif op == "addc":
                 vals[i] = vals[k[1]] + dtype(k[2])
+            elif op == "ld":
+                vals[i] = vals[k[2]]
+            elif op == "pk":
+                hv = []
+                for h in (k[1], k[2]):
+                    hv.append(np.full(N, dtype(h[1])) if h[0] == "c" else vals[h[1]] * dtype(h[2]))
+                vals[i] = (hv[0], hv[1])
+            elif op == "half":
+                vals[i] = vals[k[1]][k[2]]
+            elif op == "mul2":
+                vals[i] = (vals[k[1]][0] * vals[k[2]], vals[k[1]][1] * vals[k[2]])
+            elif op == "mul2c":
+                vals[i] = (vals[k[1]][0] * dtype(k[2]), vals[k[1]][1] * dtype(k[2]))
+            elif op == "add2":
+                a, b = vals[k[1]], vals[k[2]]
+                vals[i] = (a[0] + b[0], a[1] + b[1]) if k[3] > 0 else (a[0] - b[0], a[1] - b[1])
+            elif op == "add2k":
+                vals[i] = (vals[k[1]][0] + dtype(k[2]), vals[k[1]][1] + dtype(k[3]))
         sizes: Dict[str, int] = {}
         for name, idx, _ in self.outputs:
             sizes[name] = max(sizes.get(name, 0), idx + 1)
