@@ -76,13 +76,13 @@ def build_robot_library(robot: Robot, plan: Optional[KernelPlan] = None, force: 
     os.replace(so + ".tmp", so)
     # drop stale libraries of the same robot
     prefix = "libgrid_%s_" % robot.name
+    keep = "_%s_%s" % (robot.param_hash(), _static_hash())
     for fn in os.listdir(LIB_DIR):
-        if fn.startswith(prefix) and fn.endswith(tag + ".so") and os.path.join(LIB_DIR, fn) != so and not tag:
-            if "_" + _static_hash() not in fn or robot.param_hash() not in fn:
-                try:
-                    os.remove(os.path.join(LIB_DIR, fn))
-                except OSError:
-                    pass
+        if fn.startswith(prefix) and not tag and keep not in fn:
+            try:
+                os.remove(os.path.join(LIB_DIR, fn))
+            except OSError:
+                pass
     info = {"stats": stats, "codegen_s": t1 - t0, "nvcc_s": time.time() - t1, "ptxas": proc.stderr}
     with open(so[:-3] + ".ptxas.txt", "w") as f:
         f.write(proc.stderr)

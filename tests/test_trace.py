@@ -110,3 +110,31 @@ def test_lane_uniform_column_program(name, alg):
         ins["mq%d" % i] = np.zeros(2)
         ins["mqd%d" % i] = np.zeros(2)
     assert np.all(p.evaluate(ins, np.float64)["col"] == 0.0)
+
+
+@pytest.mark.parametrize("name", ["iiwa14", "hyq"])
+@pytest.mark.parametrize("park", [(), ("v", "mXa", "mf"), ("v", "Iv", "mXa", "mf", "Minv")])
+def test_paired_and_parked_gradient_programs(name, park):
+    """Experimental tps variants (KernelPlan.tps_pairs / tps_v2_park): the (d/dq_j, d/dqd_j) columns
+    travel as float2 pairs (FFMA2) and per-joint data can be parked in shared memory and re-loaded
+    per column.  Same numbers as the scalar trace."""
+    from gridcodegenerator_b200.algorithms import trace_fd_grad_paired, trace_id_grad_paired
+    robot = load_named_robot(name).with_damping(0.2)
+    q, qd, u, qdd = (x.astype(np.float64) for x in make_states(robot.n, 3, 13))
+    p = trace_fd_grad_paired(robot, False, park)
+    assert p.op_counts().get("packed", 0) > 0
+    assert relerr(p.evaluate(_ins(q=q, qd=qd, u=u))["df_du"], O.batch(robot, "fd_grad", q, qd, u)) < 1e-11
+    p = trace_id_grad_paired(robot, True, [x for x in park if x != "Minv"])
+    assert relerr(p.evaluate(_ins(q=q, qd=qd, qdd=qdd))["dc_du"], O.batch(robot, "id_grad", q, qd, qdd)) < 1e-11
+    if park:
+        assert len(p.parks) > 0 and any(k[0] == "ld" for k in p.nodes)
+
+
+def test_experimental_variants_emit_compilable_looking_code():
+    from gridcodegenerator_b200.codegen import emit_alg_struct_looped, emit_alg_struct_v2
+    robot = load_named_robot("iiwa14")
+    txt, cnt = emit_alg_struct_looped(robot, "AlgFdGrad", "fd_grad")
+    assert "for (int col = 0; col < 14; ++col)" in txt and cnt["loop_body_flops"] > 0
+    txt, cnt = emit_alg_struct_v2(robot, "fd_grad", ("v", "mXa", "mf"))
+    assert "__ffma2_rn(" in txt and "flush_colpair<7>(g_tile, s_warp, 6, cnt, lane);" in txt and "s_park[" in txt
+    assert cnt["park_slots"] == 84
