@@ -314,9 +314,16 @@ def run_b200_arm(a):
     except (OSError, ValueError):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic, traffic_src = None, None
+    if (a.robot, a.alg, a.batch) == (ROBOT, ALG, BATCH):
+        try:        # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_final_tps_fdgrad_traffic.json")))
+            traffic, traffic_src = tj["traffic"], tj["source"]
+        except (OSError, ValueError, KeyError):
+            pass
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-        "traffic": None,
+        "traffic": traffic, "traffic_source": traffic_src,
         "note": "FP32 SIMT (non-tensor) roofline; achieved = algorithmic flops/state (dense reference count, "
                 "SURVEY 8d) x states / launch time; peak = FFMA microbenchmark measured in this run "
                 "(theoretical %.1f)" % FP32_THEORETICAL_TFLOPS,

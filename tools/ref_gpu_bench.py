@@ -2,7 +2,7 @@
 """Reference GPU arm: times the reference's own emitted kernels (baseline/_ref/<robot>/ref_harness*,
 built by baseline/make_reference_cuh.py) on this box, next to our kernels, on identical inputs, and
 cross-checks the two outputs.  JSON lines on stdout.
-  python tools/ref_gpu_bench.py [robot] [N ...]
+  python tools/ref_gpu_bench.py [robot] [N ...]          (REF_ALGS=id,minv,fd,id_grad,fd_grad selects algorithms)
 """
 import json
 import os
@@ -18,26 +18,23 @@ from gridcodegenerator_b200 import load_named_robot                      # noqa:
 from gridcodegenerator_b200.synthetic import make_states, pack_q_qd_u    # noqa: E402
 
 
-def ours(robot, x, N, family):
+ALGS = os.environ.get("REF_ALGS", "fd_grad").split(",")
+
+
+def ours(robot, x, N, family, alg="fd_grad"):
     import torch
     from gridcodegenerator_b200.runtime import get_engine
     eng = get_engine(robot)
     n = robot.n
     if family:
         os.environ["GRID_FORCE_KERNEL"] = family
+    if family not in eng.kernel_kind(alg):
+        os.environ.pop("GRID_FORCE_KERNEL", None)
+        raise RuntimeError("no %s kernel for %s" % (family, alg))
     xin = torch.from_numpy(x).cuda()
-    out = torch.empty(N, 2 * n * n, device="cuda")
-    for _ in range(5):
-        eng.forward_dynamics_gradient_device(out, xin)
-    torch.cuda.synchronize()
-    us = []
-    for _ in range(30):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        eng.forward_dynamics_gradient_device(out, xin)
-        b.record()
-        torch.cuda.synchronize()
-        us.append(a.elapsed_time(b) * 1e3)
+    words = {"id": n, "minv": n * n, "fd": n, "id_grad": 2 * n * n, "fd_grad": 2 * n * n}[alg]
+    out = torch.empty(N, words, device="cuda")
+    us = eng.time_launches(alg, out, xin, reps=50)          # event pairs recorded in C
     os.environ.pop("GRID_FORCE_KERNEL", None)
     return float(np.median(us)), out.cpu().numpy()
 
@@ -48,15 +45,15 @@ def main():
     robot = load_named_robot(name)
     n = robot.n
     ref_dir = os.path.join(ROOT, "baseline", "_ref", name)
-    for N in sizes:
+    for N, alg in [(N, a) for N in sizes for a in ALGS]:
         q, qd, u, _ = make_states(n, N, 77)
         x = pack_q_qd_u(q, qd, u)
         ours_res = {}
-        for fam in ("tps", "wps"):
+        for fam in ("tps", "wps", "cps"):
             try:
-                t, out = ours(robot, x, N, fam)
+                t, out = ours(robot, x, N, fam, alg)
                 ours_res[fam] = out
-                print(json.dumps({"impl": "b200_" + fam, "alg": "fd_grad", "N": N, "p50_us": t,
+                print(json.dumps({"impl": "b200_" + fam, "alg": alg, "N": N, "p50_us": t,
                                   "evals_per_s": N / t * 1e6}), flush=True)
             except Exception as e:          # family not built for this robot
                 print(json.dumps({"impl": "b200_" + fam, "N": N, "skipped": str(e)[:120]}), flush=True)
@@ -71,14 +68,14 @@ def main():
                     print(json.dumps({"impl": "reference_gpu", "unavailable": path}), flush=True)
                     continue
                 p = subprocess.run([path, os.path.join(td, "in.bin"), os.path.join(td, "out.bin"), str(threads),
-                                    "30"], capture_output=True, text=True, timeout=600)
+                                    "30", alg], capture_output=True, text=True, timeout=600)
                 if p.returncode != 0:
                     print(json.dumps({"impl": "reference_gpu", "exe": exe, "threads": threads, "N": N,
                                       "failed": (p.stdout + p.stderr)[-300:]}), flush=True)
                     continue
                 line = json.loads(p.stdout.strip().splitlines()[-1])
                 line["exe"] = exe
-                ref_out = np.fromfile(os.path.join(td, "out.bin"), dtype=np.float32).reshape(N, 2 * n * n)
+                ref_out = np.fromfile(os.path.join(td, "out.bin"), dtype=np.float32).reshape(N, -1)
                 if ours_res:
                     mine = next(iter(ours_res.values()))
                     line["max_rel_diff_vs_b200"] = float(np.abs(ref_out - mine).max() / np.abs(mine).max())
