@@ -161,9 +161,30 @@ def chain64():
     write("chain64", body)
 
 
+def mixed5():
+    """Small branched robot that exercises what the named robots do not: prismatic joints, oblique
+    X_tree rotations (dense E0), non-zero damping, products of inertia, a fixed link in the middle."""
+    body = link_xml("base", 2.0, (0, 0, 0), (0.02, 0.02, 0.02))
+    specs = [  # name, type, parent link, axis, xyz, rpy, damping, mass, com, inertia diag, inertia off
+        ("j0", "revolute", "base", "z", (0.0, 0.0, 0.1), (0.3, -0.2, 0.5), 0.4, 3.0, (0.01, 0.02, 0.08), (0.03, 0.025, 0.01), (1e-3, -2e-3, 5e-4)),
+        ("j1", "prismatic", "l_j0", "y", (0.05, 0.0, 0.2), (-0.4, 0.1, 0.9), 0.1, 1.5, (0.0, 0.05, 0.0), (0.01, 0.004, 0.01), (2e-4, 1e-4, -3e-4)),
+        ("j2", "revolute", "l_j1", "x", (0.0, 0.15, 0.0), (0.7, 0.6, -0.3), 0.0, 1.0, (0.03, 0.0, 0.02), (0.004, 0.006, 0.005), (0.0, 2e-4, 1e-4)),
+        ("j3", "prismatic", "l_j1_plate", "x", (0.1, -0.05, 0.02), (0.2, 0.0, 1.2), 0.25, 0.8, (0.04, 0.01, 0.0), (0.002, 0.003, 0.003), (1e-4, 0.0, 0.0)),
+        ("j4", "revolute", "l_j3", "y", (0.12, 0.0, 0.0), (-0.9, 0.3, 0.1), 0.05, 0.6, (0.0, 0.0, 0.05), (0.002, 0.002, 0.0008), (0.0, 0.0, 1e-4)),
+    ]
+    for name, jtype, parent, axis, xyz, rpy, damp, m, com, Id, Io in specs:
+        if name == "j3":      # a fixed plate between j1's link and j3 exercises fixed-joint merging mid-tree
+            body += link_xml("l_j1_plate", 0.4, (0.0, 0.01, 0.0), (0.001, 0.001, 0.0015))
+            body += joint_xml("j1_plate_fix", "fixed", "l_j1", "l_j1_plate", (0.02, 0.03, -0.01), (0.1, 0.2, 0.3), None)
+        body += link_xml("l_" + name, m, com, Id, Io)
+        body += joint_xml(name, jtype, parent, "l_" + name, xyz, rpy, AX[axis], damping=damp)
+    write("mixed5", body)
+
+
 if __name__ == "__main__":
+    mixed5()
     iiwa14()
     hyq()
     atlas()
     chain64()
-    print("wrote iiwa14 / hyq / atlas / chain64 URDFs into", HERE)
+    print("wrote mixed5 / iiwa14 / hyq / atlas / chain64 URDFs into", HERE)

@@ -123,7 +123,7 @@ def load_urdf(path: str, name: Optional[str] = None) -> Robot:
         return parse_urdf_string(f.read(), name)
 
 
-NAMED_ROBOTS = ("iiwa14", "hyq", "atlas", "chain64")
+NAMED_ROBOTS = ("iiwa14", "hyq", "atlas", "chain64", "mixed5")
 
 
 def load_named_robot(name: str) -> Robot:

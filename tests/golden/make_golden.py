@@ -25,12 +25,16 @@ from gridcodegenerator_b200 import load_named_robot          # noqa: E402
 from gridcodegenerator_b200.synthetic import make_states, seed_for  # noqa: E402
 from reference import GRiDCodeGenerator as RefGen             # noqa: E402
 
-CASES = [("iiwa14", 0.0, 8), ("iiwa14", 0.5, 4), ("hyq", 0.0, 8), ("atlas", 0.0, 4), ("chain64", 0.0, 2)]
+CASES = [("mixed5", None, 8), ("iiwa14", 0.0, 8), ("iiwa14", 0.5, 4), ("hyq", 0.0, 8), ("atlas", 0.0, 4), ("chain64", 0.0, 2)]
 
 
 def main():
     for name, damping, N in CASES:
-        robot = load_named_robot(name).with_damping(damping)
+        robot = load_named_robot(name)
+        if damping is None:                      # keep the URDF's own per-joint damping
+            damping = -1.0
+        else:
+            robot = robot.with_damping(damping)
         g = RefGen(robot)
         n = robot.n
         q, qd, u, qdd = make_states(n, N, seed_for(name))
@@ -47,7 +51,7 @@ def main():
                 out["dc_du"].append(g.test_rnea_grad(q64[s], qd64[s]))
                 out["dc_du_qdd"].append(g.test_rnea_grad(q64[s], qd64[s], qdd64[s]))
                 out["df_du"].append(g.test_fd_grad(q64[s], qd64[s], u64[s]))
-        tag = name if damping == 0.0 else "%s_damped" % name
+        tag = name if damping <= 0.0 else "%s_damped" % name
         np.savez_compressed(os.path.join(HERE, tag + ".npz"), robot_hash=robot.param_hash(),
                             damping=damping, q=q, qd=qd, u=u, qdd=qdd,
                             **{k: np.array(v) for k, v in out.items()})

@@ -70,7 +70,7 @@ def supported(eng, alg, family=None):
     return kind != "none" if family is None else family in kind
 
 
-@pytest.mark.parametrize("tag", ["iiwa14", "iiwa14_damped", "hyq", "atlas", "chain64"])
+@pytest.mark.parametrize("tag", ["mixed5", "iiwa14", "iiwa14_damped", "hyq", "atlas", "chain64"])
 def test_against_reference_goldens(tag):
     robot, z = load_golden(tag)
     eng = get_engine(robot)
@@ -95,7 +95,7 @@ def test_against_reference_goldens(tag):
     assert ran == set(ALL), "every algorithm must have a kernel for %s, got %s" % (tag, sorted(ran))
 
 
-@pytest.mark.parametrize("name,N", [("iiwa14", 256), ("hyq", 256), ("atlas", 64), ("chain64", 8)])
+@pytest.mark.parametrize("name,N", [("iiwa14", 256), ("hyq", 256), ("atlas", 64), ("chain64", 8), ("mixed5", 256)])
 @pytest.mark.parametrize("family", FAMILIES)
 @pytest.mark.parametrize("alg", ALL)
 def test_against_oracle_seeded_states(name, N, alg, family):
@@ -200,7 +200,7 @@ def test_host_path_grid_data():
 
 
 @pytest.mark.parametrize("name,N,algs", [("iiwa14", 65536, ALL), ("hyq", 16384, ALL), ("atlas", 4096, ALL),
-                                         ("chain64", 256, ALL)])
+                                         ("chain64", 256, ALL), ("mixed5", 8192, ALL)])
 def test_full_batches_against_c_oracle(name, N, algs):
     """BASELINE.json batch sizes, every state checked: the C restatement of the oracle
     (oracle/rbd_oracle.c, pinned to the reference goldens in tests/test_oracle.py) finishes

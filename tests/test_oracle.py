@@ -11,7 +11,7 @@ import pytest
 from helpers import load_golden, relerr
 from oracle import rbd_numpy as O
 
-TAGS = ["iiwa14", "iiwa14_damped", "hyq", "atlas", "chain64"]
+TAGS = ["mixed5", "iiwa14", "iiwa14_damped", "hyq", "atlas", "chain64"]
 
 
 @pytest.mark.parametrize("tag", TAGS)
@@ -80,7 +80,7 @@ def test_oracle_matches_live_reference(name):
     assert relerr(O.rnea_grad(robot, q, qd), ref_dc) < 1e-11
 
 
-@pytest.mark.parametrize("tag", ["iiwa14_damped", "hyq", "atlas", "chain64"])
+@pytest.mark.parametrize("tag", ["mixed5", "iiwa14_damped", "hyq", "atlas", "chain64"])
 def test_c_oracle_matches_numpy_oracle_and_goldens(tag):
     from helpers import colmajor_batch
     from oracle import c_oracle as C

@@ -43,10 +43,12 @@ def _run(robot, key, q, qd, u, qdd, dtype):
     raise KeyError(key)
 
 
-@pytest.mark.parametrize("name", ["iiwa14", "hyq"])
+@pytest.mark.parametrize("name", ["iiwa14", "hyq", "mixed5"])
 @pytest.mark.parametrize("key", list(TRACERS))
 def test_traced_program_matches_oracle(name, key):
-    robot = load_named_robot(name).with_damping(0.3)
+    robot = load_named_robot(name)
+    if name != "mixed5":
+        robot = robot.with_damping(0.3)
     q, qd, u, qdd = (x.astype(np.float64) for x in make_states(robot.n, 4, 11))
     out, ref, alg = _run(robot, key, q, qd, u, qdd, np.float64)
     assert relerr(out, ref) < 1e-11
