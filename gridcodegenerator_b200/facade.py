@@ -216,9 +216,9 @@ class GRiDCodeGenerator:
 
     # ------------------------------------------------------------------ topology helpers (python values)
     def gen_topology_helpers_size(self):
-        """The reference stores a run-time int table (helpers/_topology_helpers.py:184-191);
-        topology is resolved at trace time here, so nothing is stored."""
-        return 0
+        """Ints in the emitted topology table (fixed layout, see _topology_table).  The traced
+        programs do not read it: topology is resolved at trace time."""
+        return 6 * self.robot.get_num_pos() + 1
 
     def gen_topology_sparsity_helpers_python(self, INIT_MODE=False):
         """Same python values as helpers/_topology_helpers.py:193-215."""
@@ -302,18 +302,143 @@ class GRiDCodeGenerator:
             "};", ""])
 
     def gen_spatial_algebra_helpers(self):
-        """The reference emits ~35 dot_prod / mx* / fx* device helpers here
-        (helpers/_spatial_algebra_helpers.py:35-256).  Spatial algebra is folded into the traced
-        programs, so only a note is emitted."""
-        self.gen_add_code_line("// spatial algebra (mx*, fx*, X, I products) is folded into the traced per-robot programs")
+        """dot_prod, mx0..mx5 (+_peq/_scaled/_peq_scaled), mxX*, fx, fx_zeroed, fx_times_v(_peq) with the
+        reference's names and signatures (helpers/_spatial_algebra_helpers.py:35-256), for user code
+        written against them.  The traced programs do not call them: their cross products are folded
+        at trace time.  Entries are generated from the definition (v x) = [[w x, 0], [l x, w x]],
+        fx = -(v x)^T."""
+        L = self.gen_add_code_line
+        L("// spatial algebra helpers kept for API compatibility (the traced programs fold these away)")
+        L("template <typename T, int N, int S1, int S2, typename P1, typename P2>")
+        L("__device__ T dot_prod(const P1 *vec1, const P2 *vec2) {")
+        L("    T result = 0;")
+        L("    for (int i = 0; i < N; i++) { result += vec1[i*S1] * vec2[i*S2]; }")
+        L("    return result;")
+        L("}")
+
+        def skew_entry(r, c, base):
+            """(a x)[r][c] as (sign, component index) or None, for the 3-vector stored at offset base."""
+            if r == c:
+                return None
+            k = 3 - r - c
+            sign = 1 if (c - r) % 3 == 2 else -1      # [[0,-a2,a1],[a2,0,-a0],[-a1,a0,0]]
+            return sign, base + k
+
+        def crm_entry(r, c):
+            """motion cross matrix (v x)[r][c]"""
+            if r < 3 and c < 3:
+                return skew_entry(r, c, 0)
+            if r >= 3 and c >= 3:
+                return skew_entry(r - 3, c - 3, 0)
+            if r >= 3 and c < 3:
+                return skew_entry(r - 3, c, 3)
+            return None
+
+        def term(e, vec):
+            return "static_cast<T>(0)" if e is None else "%s%s[%d]" % ("-" if e[0] < 0 else "", vec, e[1])
+
+        for k in range(6):
+            col = [crm_entry(r, k) for r in range(6)]
+            for peq, scaled in ((False, False), (True, False), (False, True), (True, True)):
+                name = "mx%d%s%s" % (k, "_peq" if peq else "", "_scaled" if scaled else "")
+                L("template <typename T>")
+                L("__device__ void %s(T *s_vecX, const T *s_vec%s) {" % (name, ", const T alpha" if scaled else ""))
+                for r in range(6):
+                    if col[r] is None and peq:
+                        continue
+                    L("    s_vecX[%d] %s %s%s;" % (r, "+=" if peq else "=", term(col[r], "s_vec"),
+                                                  "*alpha" if scaled and col[r] is not None else ""))
+                L("}")
+        for peq, scaled in ((False, False), (True, False), (False, True), (True, True)):
+            suffix = ("_peq" if peq else "") + ("_scaled" if scaled else "")
+            L("template <typename T>")
+            L("__device__ void mxX%s(T *s_vecX, const T *s_vec, %sconst int S_ind) {" % (
+                suffix, "const T alpha, " if scaled else ""))
+            L("    switch(S_ind){")
+            for k in range(6):
+                L("        case %d: mx%d%s<T>(s_vecX, s_vec%s); break;" % (k, k, suffix, ", alpha" if scaled else ""))
+            L("    }")
+            L("}")
+        fx_entry = lambda r, c: (lambda e: None if e is None else (-e[0], e[1]))(crm_entry(c, r))   # fx = -(v x)^T
+        for zeroed in (False, True):
+            L("template <typename T>")
+            L("__device__ void fx%s(T *s_matX, const T *s_vecX) {" % ("_zeroed" if zeroed else ""))
+            for c in range(6):
+                for r in range(6):
+                    e = fx_entry(r, c)
+                    if e is None and zeroed:
+                        continue
+                    L("    s_matX[6*%d + %d] = %s;" % (c, r, term(e, "s_vecX")))
+            L("}")
+        for peq in (False, True):
+            L("template <typename T>")
+            L("__device__ void fx_times_v%s(T *s_result, const T *s_fxVec, const T *s_timesVec) {" % ("_peq" if peq else ""))
+            for r in range(6):
+                terms = []
+                for c in range(6):
+                    e = fx_entry(r, c)
+                    if e is not None:
+                        terms.append("%s s_fxVec[%d] * s_timesVec[%d]" % ("-" if e[0] < 0 else "+", e[1], c))
+                L("    s_result[%d] %s %s;" % (r, "+=" if peq else "=", " ".join(terms)))
+            L("}")
+        L("")
 
     def gen_mx_func_call_for_cpp(self, inds=None, PEQ_FLAG=False, SCALE_FLAG=False, updated_var_names=None):
-        raise NotImplementedError("mx* device helpers are not emitted: cross products are folded at trace time "
-                                  "(see gridcodegenerator_b200/algorithms.py cross_motion_axis)")
+        """Emits the call to the statically selected mx<k> helper when all joints in `inds` share an axis,
+        else to the run-time mxX variant (helpers/_spatial_algebra_helpers.py:1-33)."""
+        v = dict(S_ind_name="S_ind", s_dst_name="s_dst", s_src_name="s_src", s_scale_name="s_scale")
+        v.update(updated_var_names or {})
+        n = self.robot.get_num_pos()
+        inds = list(range(n)) if inds is None else inds
+        same = self.robot.are_Ss_identical(inds)
+        k = str(self.robot.S_ind[inds[0]]) if same else "X"
+        name = "mx%s%s%s<T>" % (k, "_peq" if PEQ_FLAG else "", "_scaled" if SCALE_FLAG else "")
+        args = [v["s_dst_name"], v["s_src_name"]] + ([v["s_scale_name"]] if SCALE_FLAG else []) + \
+               ([] if same else [v["S_ind_name"]])
+        self.gen_add_code_line("%s(%s);" % (name, ", ".join(args)))
+
+    def _topology_table(self):
+        """[parent(n) | S_ind(n) | num_ancestors(n) | num_subtree(n) | running_sum_anc(n+1) | running_sum_sub(n)]"""
+        n = self.robot.get_num_pos()
+        num_anc = [len(self.robot.get_ancestors_by_id(j)) for j in range(n)]
+        num_sub = [len(self.robot.get_subtree_by_id(j)) for j in range(n)]
+        run_anc = [sum(num_anc[:j]) for j in range(n + 1)]
+        run_sub = [sum(num_sub[:j]) for j in range(n)]
+        return list(self.robot.get_parent_id_array()) + list(self.robot.S_ind) + num_anc + num_sub + run_anc + run_sub
 
     def gen_topology_helpers_pointers_for_cpp(self, inds=None, updated_var_names=None, NO_GRAD_FLAG=False):
-        raise NotImplementedError("no run-time topology table exists: parents, subtrees and column offsets are "
-                                  "resolved at trace time (see gridcodegenerator_b200/algorithms.py)")
+        """C++ index expressions for parent / S axis / compressed-column offsets of joint `jid`
+        (helpers/_topology_helpers.py:260-332): literals for a single joint, closed forms for serial
+        chains, otherwise look-ups in the emitted `topology_helpers` table (a namespace-scope device
+        array here; the same layout is also reachable through robotModel::d_topology_helpers)."""
+        v = dict(jid_name="jid", s_topology_helpers_name="topology_helpers")
+        v.update(updated_var_names or {})
+        n = self.robot.get_num_pos()
+        inds = list(range(n)) if inds is None else inds
+        jid, tab = v["jid_name"], v["s_topology_helpers_name"]
+        _, _, run_dva, _, _, run_df, df_col = self.gen_topology_sparsity_helpers_python()
+        same_S = self.robot.are_Ss_identical(inds)
+        if len(inds) == 1:
+            i, par = inds[0], self.robot.get_parent_id(inds[0])
+            dva_p1 = run_dva[i + 1] if i + 1 < n else run_dva[i] + len(self.robot.get_ancestors_by_id(i)) + 1
+            out = [str(par), str(self.robot.S_ind[i]), str(run_dva[i]), str(run_df[i]),
+                   str(run_dva[par]) if par >= 0 else "-1", str(run_df[par]) if par >= 0 else "-1", str(dva_p1),
+                   str(df_col[i])]
+        elif self.robot.is_serial_chain():
+            out = ["(%s-1)" % jid, str(self.robot.S_ind[inds[0]]) if same_S else "%s[%d + %s]" % (tab, n, jid),
+                   "%s*(%s+1)/2" % (jid, jid), "%d*%s" % (n, jid), "%s*(%s-1)/2" % (jid, jid), "%d*(%s-1)" % (n, jid),
+                   "(%s+1)*(%s+2)/2" % (jid, jid), jid]
+        else:
+            par = "%s[%s]" % (tab, jid)
+            ra, rs = 4 * n, 5 * n + 1
+            out = [par, str(self.robot.S_ind[inds[0]]) if same_S else "%s[%d + %s]" % (tab, n, jid),
+                   "(%s[%d + %s] + %s)" % (tab, ra, jid, jid),
+                   "(%s[%d + %s] + %s[%d + %s])" % (tab, ra, jid, tab, rs, jid),
+                   "(%s[%d + %s] + %s)" % (tab, ra, par, par),
+                   "(%s[%d + %s] + %s[%d + %s])" % (tab, ra, par, tab, rs, par),
+                   "(%s[%d + %s + 1] + %s + 1)" % (tab, ra, jid, jid),
+                   "%s[%d + %s]" % (tab, 2 * n, jid)]
+        return tuple(out[:2]) if NO_GRAD_FLAG else tuple(out)
 
     def gen_insert_helpers_function_call(self, updated_var_names=None):
         """Argument splice for the helper pointers every *_inner takes.  There is no topology
@@ -331,7 +456,16 @@ class GRiDCodeGenerator:
         return func_def, func_params
 
     def gen_init_topology_helpers(self):
-        self.gen_add_code_line("// topology (parents, subtrees, ancestor sets) is compiled in: no run-time table")
+        tab = self._topology_table()
+        self.gen_add_code_lines([
+            "// topology table for user code (the traced programs resolve topology at generation time):",
+            "// [parent(n) | S_ind(n) | num_ancestors(n) | num_subtree(n) | running_sum_anc(n+1) | running_sum_sub(n)]",
+            "__device__ const int topology_helpers[%d] = {%s};" % (len(tab), ", ".join(str(x) for x in tab)),
+            "const int h_topology_helpers[%d] = {%s};" % (len(tab), ", ".join(str(x) for x in tab)),
+            "template <typename T>", "__host__", "int *init_topology_helpers(){",
+            "    int *d_topology_helpers; gpuErrchk(cudaMalloc((void**)&d_topology_helpers,%d*sizeof(int)));" % len(tab),
+            "    gpuErrchk(cudaMemcpy(d_topology_helpers,h_topology_helpers,%d*sizeof(int),cudaMemcpyHostToDevice));" % len(tab),
+            "    return d_topology_helpers;", "}", ""])
 
     def gen_init_XImats(self, include_base_inertia=False):
         self.gen_add_code_line("// X_tree and inertia constants are immediates of the traced programs: no XI table")
@@ -341,7 +475,8 @@ class GRiDCodeGenerator:
                               "A pointer to the robotModel struct on the GPU")
         self.gen_add_code_lines([
             "template <typename T>", "__host__", "robotModel<T>* init_robotModel() {",
-            "    robotModel<T> h_robotModel; h_robotModel.d_XImats = nullptr; h_robotModel.d_topology_helpers = nullptr;",
+            "    robotModel<T> h_robotModel; h_robotModel.d_XImats = nullptr;",
+            "    h_robotModel.d_topology_helpers = init_topology_helpers<T>();",
             "    robotModel<T> *d_robotModel; gpuErrchk(cudaMalloc((void**)&d_robotModel,sizeof(robotModel<T>)));",
             "    gpuErrchk(cudaMemcpy(d_robotModel,&h_robotModel,sizeof(robotModel<T>),cudaMemcpyHostToDevice));",
             "    return d_robotModel;", "}", ""])

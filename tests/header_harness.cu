@@ -3,7 +3,8 @@
 // functions on state 0.  argv: <input.bin> <output.bin>
 // input : int32 N, float q_qd_u[N*3n], float qdd[N*n]
 // output: c, c_qdd, Minv, fd_qdd, dc_du, dc_du_qdd, df_du, df_du_pre, df_du_compute_only  (N states each)
-//         then device-function results for state 0: df_du_dev, dc_du_inner, Minv_inner, qdd_finish, c_inner
+//         then device-function results for state 0: df_du_dev, dc_du_inner, Minv_inner, qdd_finish, c_inner,
+//         mxX(v1, k) for k = 0..5 (column 2 tripled), fx_times_v(v1, f1), fx(v1) * f1 via dot_prod
 #include "grid.cuh"
 #include <vector>
 using namespace grid;
@@ -36,6 +37,18 @@ __global__ void device_fn_kernel(T *out, const T *q_qd_u, const T *qdd_in, const
     inverse_dynamics_device<T>(s_c, s_q, s_qd, d_robotModel, gravity);
     forward_dynamics_finish<T>(s_fin, s_u, s_c, s_Minv);
     for (int i = threadIdx.x; i < n; i += blockDim.x) { o[i] = s_fin[i]; o[n + i] = s_c[i]; }
+    o += 2 * n;
+    __syncthreads();
+    // spatial algebra helpers: (v x) e_k for k = 0..5 via mxX, v x* f via fx_times_v and via fx + dot_prod
+    if (threadIdx.x == 0) {
+        const T *v = s_vaf + 6, *f = s_vaf + 12 * n + 6;          // v and f of joint 1
+        for (int k = 0; k < 6; k++) mxX<T>(o + 6 * k, v, k);
+        mx2_peq_scaled<T>(o + 12, v, static_cast<T>(2));           // column 2 becomes 3 * mx2(v)
+        fx_times_v<T>(o + 36, v, f);
+        T M[36];
+        fx<T>(M, v);
+        for (int r = 0; r < 6; r++) o[42 + r] = dot_prod<T, 6, 6, 1>(M + r, f);
+    }
 }
 
 #endif
@@ -90,7 +103,7 @@ int main(int argc, char **argv) {
     dump(hd->h_df_du, size_t(N) * 2 * n * n);
 
 #ifdef HARNESS_DEVICE_FNS
-    const size_t dev_words = 2 * n * n * 2 + n * n + 2 * n;
+    const size_t dev_words = 2 * n * n * 2 + n * n + 2 * n + 48;
     float *d_dev;
     gpuErrchk(cudaMalloc(&d_dev, dev_words * sizeof(float)));
     device_fn_kernel<float><<<1, 64>>>(d_dev, hd->d_q_qd_u, hd->d_qdd, hd->d_Minv, d_robotModel, gravity);

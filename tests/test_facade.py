@@ -36,6 +36,27 @@ def test_constructor_and_sizes():
     assert dva == 28 and df == 49 and dva_per == [1, 2, 3, 4, 5, 6, 7]
 
 
+def test_topology_pointer_strings():
+    chain = GRiDCodeGenerator(load_named_robot("iiwa14"))
+    par, S, dva, df, dva_p, df_p, dva_p1, dfc = chain.gen_topology_helpers_pointers_for_cpp()
+    assert (par, S, dva, df, dfc) == ("(jid-1)", "2", "jid*(jid+1)/2", "7*jid", "jid")        # closed forms
+    tree = GRiDCodeGenerator(load_named_robot("hyq"))
+    par, S = tree.gen_topology_helpers_pointers_for_cpp(NO_GRAD_FLAG=True)
+    assert par == "topology_helpers[jid]" and S == "topology_helpers[12 + jid]"
+    one = tree.gen_topology_helpers_pointers_for_cpp(inds=[4])
+    assert one[0] == "3" and one[1] == "1"
+    tab = tree._topology_table()
+    assert len(tab) == tree.gen_topology_helpers_size() == 73 and tab[:12] == load_named_robot("hyq").parent
+    # the expressions index the table consistently with the python-side sparsity helpers
+    _, _, run_dva, _, _, run_df, df_col = tree.gen_topology_sparsity_helpers_python()
+    full = tree.gen_topology_helpers_pointers_for_cpp()
+    env = {"topology_helpers": tab}
+    for jid in range(12):
+        env["jid"] = jid
+        assert eval(full[2], {}, env) == run_dva[jid] and eval(full[3], {}, env) == run_df[jid]
+        assert eval(full[7], {}, env) == df_col[jid]
+
+
 def test_emitter_helpers_append_to_code_str():
     g = GRiDCodeGenerator(load_named_robot("iiwa14"))
     g.gen_add_code_line("int x = 0;")
@@ -47,6 +68,11 @@ def test_emitter_helpers_append_to_code_str():
                           "ind += blockDim.x*blockDim.y){\n    x += ind;\n}\n__syncthreads();\n")
     g.gen_forward_dynamics_finish_function_call()
     assert "forward_dynamics_finish<T>(s_qdd, s_u, s_c, s_Minv);" in g.code_str
+    g.gen_mx_func_call_for_cpp(PEQ_FLAG=True, SCALE_FLAG=True, updated_var_names=dict(s_dst_name="s_a", s_src_name="s_v", s_scale_name="s_qd[k]"))
+    assert "mx2_peq_scaled<T>(s_a, s_v, s_qd[k]);" in g.code_str          # iiwa14: every joint about z
+    h = GRiDCodeGenerator(load_named_robot("hyq"))
+    h.gen_mx_func_call_for_cpp()
+    assert "mxX<T>(s_dst, s_src, S_ind);" in h.code_str                    # mixed axes: run-time variant
 
 
 @pytest.mark.parametrize("name", ["iiwa14", "hyq"])
@@ -137,4 +163,12 @@ def test_emitted_header_host_and_device_functions_on_gpu(tmp_path):
     assert relerr(take(n * n, 1)[0], O.colmajor(O.minv(robot, q64[0], dense=False))) < TOL["minv"]
     assert relerr(take(n, 1)[0], fdq) < TOL["fd"]                              # forward_dynamics_finish
     assert relerr(take(n, 1)[0], O.rnea(robot, q64[0], qd64[0])[0]) < TOL["id"]
+    # spatial algebra helpers on (v_1, f_1) of state 0 at qdd = FD's qdd
+    _, v, _, f = O.rnea(robot, q64[0], qd64[0], fdq)
+    mx = take(36, 1)[0].reshape(6, 6)
+    for k in range(6):
+        expect = O.cross_motion_axis(k, v[:, 1]) * (3.0 if k == 2 else 1.0)
+        assert np.allclose(mx[k], expect, rtol=1e-4, atol=1e-5), k
+    assert np.allclose(take(6, 1)[0], O.cross_force(v[:, 1], f[:, 1]), rtol=1e-4, atol=1e-4)
+    assert np.allclose(take(6, 1)[0], O.cross_force(v[:, 1], f[:, 1]), rtol=1e-4, atol=1e-4)
     assert pos == data.size
