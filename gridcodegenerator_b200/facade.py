@@ -274,7 +274,8 @@ class GRiDCodeGenerator:
         warps = self._suggested_threads() // 32
         sizes = {"ID": (3 * n, n), "MINV": (n, n * n), "FD": (3 * n, n), "ID_DU": (3 * n, 2 * n * n),
                  "FD_DU": (3 * n + n * n, 2 * n * n)}
-        return {k: warps * 32 * max(i | 1, o | 1) for k, (i, o) in sizes.items()}
+        # upper bound of csrc/grid_tps.cuh TpsShape::WARP_WORDS over the variants of each code
+        return {k: warps * ((32 * max(i | 1, o | 1) + 3) // 4 * 4) for k, (i, o) in sizes.items()}
 
     def _suggested_threads(self) -> int:
         return 128
