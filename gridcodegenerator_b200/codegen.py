@@ -443,7 +443,7 @@ def wps_layout(robot: Robot) -> Dict[str, object]:
                 save=save, dfbase=dfbase, smem_bytes=4 * total)
 
 
-def emit_wps_tables(robot: Robot, lay: Dict[str, object]) -> str:
+def emit_wps_tables(robot: Robot, lay: Dict[str, object], include: bool = True) -> str:
     n = robot.n
 
     def ints(name, vals):
@@ -472,7 +472,8 @@ def emit_wps_tables(robot: Robot, lay: Dict[str, object]) -> str:
     t.append(floats("wt_I_g", [x for i in range(n) for x in robot.Imats[i].flatten()]).replace("__constant__", "__device__ const"))
     t.append(floats("wt_damping", robot.damping))
     t.append("}}  // namespace GRID_NS::gen\n")
-    t.append('#include "grid_wps.cuh"\n')
+    if include:
+        t.append('#include "grid_wps.cuh"\n')
     return "".join(t)
 
 

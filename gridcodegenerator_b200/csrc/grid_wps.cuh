@@ -512,9 +512,9 @@ __device__ void grad_column(float *s, int col, bool valid) {
 // ALG: 0 = Minv, 1 = FD, 2 = ID gradient, 3 = FD gradient.
 // EXTRA: ALG 2 -> qdd given (USE_QDD_FLAG); ALG 3 -> qdd and Minv given (USE_QDD_MINV_FLAG).
 template <int ALG, bool EXTRA>
-__global__ void __launch_bounds__(NT)
-wps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in, int stride, const float *__restrict__ d_qdd,
-           const float *__restrict__ d_Minv, int num_states, float gravity) {
+__device__ __forceinline__ void wps_body(float *__restrict__ d_out, const float *__restrict__ d_in, int stride,
+                                         const float *__restrict__ d_qdd, const float *__restrict__ d_Minv,
+                                         int num_states, float gravity) {
     extern __shared__ float4 smem4[];
     float *s = reinterpret_cast<float *>(smem4);
     const int tid = threadIdx.x;
@@ -607,6 +607,18 @@ wps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in, int stride
         }
         __syncthreads();
     }
+}
+
+}}  // namespace GRID_NS::wps
+
+namespace GRID_NS { namespace wps {
+
+// needs blockDim.x == WT::NT threads and L::total floats of dynamic shared memory
+template <int ALG, bool EXTRA>
+__global__ void __launch_bounds__(NT)
+wps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in, int stride, const float *__restrict__ d_qdd,
+           const float *__restrict__ d_Minv, int num_states, float gravity) {
+    wps_body<ALG, EXTRA>(d_out, d_in, stride, d_qdd, d_Minv, num_states, gravity);
 }
 
 }}  // namespace GRID_NS::wps

@@ -30,7 +30,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from . import algorithms as A
-from .codegen import _flit, emit_alg_struct, KernelPlan, VARIANTS
+from .codegen import _flit, emit_alg_struct, emit_wps_tables, KernelPlan, VARIANTS
 from .ir import Program
 from .robot import Robot
 
@@ -99,6 +99,10 @@ class GRiDCodeGenerator:
         self.file_namespace = FILE_NAMESPACE
         self._plan = KernelPlan(self.robot)
         self._impl_ns = "%s_b200_impl" % FILE_NAMESPACE
+        # kernel family behind each emitted kernel: straight-line thread-per-state where the traced
+        # program is small enough, else the wide CTA-per-state kernels
+        self._family = {a: ("tps" if "tps" in k else "wps" if "wps" in k else None) for a, k in self._plan.kind.items()}
+        self._unsupported = {a for a, f in self._family.items() if f != "tps"}
 
     # ------------------------------------------------------------------ text emitter helpers
     def gen_add_code_line(self, new_code_line, add_indent_after=False):
@@ -271,14 +275,19 @@ class GRiDCodeGenerator:
     def _shared_counts(self) -> Dict[str, int]:
         """Dynamic shared memory (floats) the emitted kernels need for SUGGESTED_THREADS threads."""
         n = self.robot.get_num_pos()
-        warps = self._suggested_threads() // 32
+        warps = max(1, self._suggested_threads() // 32)
         sizes = {"ID": (3 * n, n), "MINV": (n, n * n), "FD": (3 * n, n), "ID_DU": (3 * n, 2 * n * n),
                  "FD_DU": (3 * n + n * n, 2 * n * n)}
         # upper bound of csrc/grid_tps.cuh TpsShape::WARP_WORDS over the variants of each code
-        return {k: warps * ((32 * max(i | 1, o | 1) + 3) // 4 * 4) for k, (i, o) in sizes.items()}
+        out = {k: warps * ((32 * max(i | 1, o | 1) + 3) // 4 * 4) for k, (i, o) in sizes.items()}
+        for code, alg in (("MINV", "minv"), ("FD", "fd"), ("ID_DU", "id_grad"), ("FD_DU", "fd_grad")):
+            if self._family[alg] == "wps":
+                out[code] = self._plan.wps["smem_bytes"] // 4
+        return out
 
     def _suggested_threads(self) -> int:
-        return 128
+        """Block size of the emitted kernels: the wide kernels need exactly WT::NT threads."""
+        return self._plan.wps["NT"] if "wps" in self._family.values() else 128
 
     def gen_add_constants_helpers(self):
         n = self.robot.get_num_pos()
@@ -513,19 +522,24 @@ class GRiDCodeGenerator:
                                  "const robotModel<T> *d_robotModel, T *s_temp) {}", ""])
 
     def gen_init_close_grid(self):
-        if self._unsupported & {"id_grad", "fd_grad"}:
-            self.gen_add_code_line("// gradient kernels are not part of this header build (robot too large for the "
-                                   "single-thread programs); use libgrid_<robot>.so")
+        if None in self._family.values():
+            self.gen_add_code_line("// some kernels do not exist for this robot: init_grid/close_grid omitted")
             return
         self.gen_add_func_doc("Sets shared mem needed for gradient kernels and initializes streams for host functions",
                               [], [], "A pointer to the array of streams")
         self.gen_add_code_lines([
             "template <typename T>", "__host__", "cudaStream_t *init_grid(){",
-            "    // the gradient kernels may need more than the default 48 KB of dynamic shared memory",
+            "    // kernels may need more than the default 48 KB of dynamic shared memory",
+            "    typedef void (*k5_t)(T *, const T *, const int, const robotModel<T> *, const int);",
             "    typedef void (*k6_t)(T *, const T *, const int, const robotModel<T> *, const T, const int);",
             "    typedef void (*k7_t)(T *, const T *, const int, const T *, const robotModel<T> *, const T, const int);",
             "    typedef void (*k8_t)(T *, const T *, const int, const T *, const T *, const robotModel<T> *, const T, const int);",
+            "    const int minv_bytes = MINV_DYNAMIC_SHARED_MEM_COUNT*sizeof(T), fd_bytes = FD_DYNAMIC_SHARED_MEM_COUNT*sizeof(T);",
             "    const int id_du_bytes = ID_DU_MAX_SHARED_MEM_COUNT*sizeof(T), fd_du_bytes = FD_DU_MAX_SHARED_MEM_COUNT*sizeof(T);",
+            "    gpuErrchk(cudaFuncSetAttribute(static_cast<k5_t>(&direct_minv_kernel<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,minv_bytes));",
+            "    gpuErrchk(cudaFuncSetAttribute(static_cast<k5_t>(&direct_minv_kernel_single_timing<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,minv_bytes));",
+            "    gpuErrchk(cudaFuncSetAttribute(static_cast<k6_t>(&forward_dynamics_kernel<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,fd_bytes));",
+            "    gpuErrchk(cudaFuncSetAttribute(static_cast<k6_t>(&forward_dynamics_kernel_single_timing<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,fd_bytes));",
             "    gpuErrchk(cudaFuncSetAttribute(static_cast<k6_t>(&inverse_dynamics_gradient_kernel<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,id_du_bytes));",
             "    gpuErrchk(cudaFuncSetAttribute(static_cast<k7_t>(&inverse_dynamics_gradient_kernel<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,id_du_bytes));",
             "    gpuErrchk(cudaFuncSetAttribute(static_cast<k6_t>(&inverse_dynamics_gradient_kernel_single_timing<T>),cudaFuncAttributeMaxDynamicSharedMemorySize,id_du_bytes));",
@@ -556,16 +570,17 @@ class GRiDCodeGenerator:
         self.gen_add_code_line("#define GRID_NS %s" % self._impl_ns)
         self.code_str += text
         self.gen_add_code_line("namespace GRID_NS { namespace gen {")
-        self._unsupported = set()
         for alg, variants in (("id", ("id", "id_qdd")), ("minv", ("minv",)), ("fd", ("fd",)),
                               ("id_grad", ("id_grad", "id_grad_qdd")), ("fd_grad", ("fd_grad", "fd_grad_qdd_minv"))):
-            if "tps" not in self._plan.kind[alg]:
-                self._unsupported.add(alg)
+            if self._family[alg] != "tps":
                 continue
             for v in variants:
                 txt, _ = emit_alg_struct(self.robot, v)
                 self.code_str += txt
         self.gen_add_code_line("}}  // namespace GRID_NS::gen")
+        if "wps" in self._family.values():
+            self.code_str += emit_wps_tables(self.robot, self._plan.wps, include=False)
+            self.code_str += open(os.path.join(_PKG, "csrc", "grid_wps.cuh")).read().replace("#pragma once", "")
         self.gen_add_code_line("#undef GRID_NS")
         self.gen_add_code_line("")
 
@@ -600,7 +615,7 @@ class GRiDCodeGenerator:
         return f
 
     def _too_large(self, alg_key, fn):
-        if alg_key in getattr(self, "_unsupported", set()) or "tps" not in self._plan.kind[alg_key]:
+        if self._family[alg_key] != "tps":
             self.gen_add_code_line("// %s: the traced single-thread program is too large for this robot; use the "
                                    "%s kernel / host function (wide CTA-per-state kernels) instead" % (fn, alg_key))
             return True
@@ -652,9 +667,8 @@ class GRiDCodeGenerator:
     def _kernel(self, name, out, in_name, stride_name, extra_params, struct_plain, struct_extra, extra_cond,
                 single_call_timing, alg_key, doc):
         """Reference-signature __global__ wrapper around the thread-per-state tile loop."""
-        if alg_key in self._unsupported:
-            self.gen_add_code_line("// %s: not emitted for this robot in the header build (wide kernels ship in "
-                                   "libgrid_<robot>.so, see INTEGRATION.md)" % name)
+        if self._family[alg_key] is None:
+            self.gen_add_code_line("// %s: no kernel for this robot (shared memory of the wide kernels exceeds 227 KB)" % name)
             return
         ns = self._impl_ns
         fn = name + ("_single_timing" if single_call_timing else "")
@@ -662,10 +676,28 @@ class GRiDCodeGenerator:
                  "const int NUM_TIMESTEPS" % (out, in_name, stride_name, extra_params)
         if name == "direct_minv_kernel":
             params = params.replace("const T gravity, ", "")
-        self.gen_add_func_doc(doc, ["one thread per state; any 1-D/2-D launch shape; dynamic shared memory = "
-                                    "<CODE>_DYNAMIC_SHARED_MEM_COUNT*sizeof(T)"], [], None)
+        wide = self._family[alg_key] == "wps"
+        self.gen_add_func_doc(doc, ["one CTA per state, lanes = columns: launch with exactly SUGGESTED_THREADS threads"
+                                    if wide else "one thread per state; any 1-D/2-D launch shape",
+                                    "dynamic shared memory = <CODE>_DYNAMIC_SHARED_MEM_COUNT*sizeof(T)"], [], None)
         self.gen_add_code_lines(["template <typename T>", "__global__", "__launch_bounds__(SUGGESTED_THREADS)",
                                  "void %s(%s) {" % (fn, params)])
+        if wide:
+            code = {"minv": 0, "fd": 1, "id_grad": 2, "fd_grad": 3}[alg_key]
+            in1 = "d_qdd" if "d_qdd" in extra_params else "nullptr"
+            in2 = "d_Minv" if "d_Minv" in extra_params else "nullptr"
+            g = "0.f" if name == "direct_minv_kernel" else "gravity"
+            call = "%s::wps::wps_body<%d, %s>(%s, %s, %s, %s, %s, %s, %s);" % (
+                ns, code, "true" if extra_cond else "false", out, in_name, stride_name, in1, in2,
+                "1" if single_call_timing else "NUM_TIMESTEPS", g)
+            body = ["    static_assert(std::is_same<T,float>::value, \"T must be float\");",
+                    "    if (blockDim.x != SUGGESTED_THREADS) { if (threadIdx.x == 0 && blockIdx.x == 0) "
+                    "printf(\"%s needs SUGGESTED_THREADS threads per block\\n\"); return; }" % fn]
+            if single_call_timing:
+                body.append("    for (int rep = 0; rep < NUM_TIMESTEPS; rep++)")
+            body.append("    " + call)
+            self.gen_add_code_lines(body + ["}", ""])
+            return
         struct = struct_extra if extra_cond else struct_plain
         in1 = "d_qdd" if "d_qdd" in extra_params else "nullptr"
         in2 = "d_Minv" if "d_Minv" in extra_params else "nullptr"
@@ -685,8 +717,9 @@ class GRiDCodeGenerator:
 
     def _host(self, fn, mode, tmpl, flags_doc, alg_key, copies_in, kernel_calls, out_name, out_words, code, takes_g=True):
         single, compute_only = mode == 1, mode == 2
-        if alg_key in self._unsupported:
+        if self._family[alg_key] is None:
             return
+        wide = self._family[alg_key] == "wps"
         name = fn + ("_single_timing" if single else "_compute_only" if compute_only else "")
         sig = "void %s(gridData<T> *hd_data, const robotModel<T> *d_robotModel, %sconst int num_timesteps, " \
               "const dim3 block_dimms, const dim3 thread_dimms%s) {" % (
@@ -697,7 +730,8 @@ class GRiDCodeGenerator:
                                "chosen by the library", flags_doc], [], None)
         T = "1" if single else "num_timesteps"
         lines = [tmpl, "__host__", sig, "    const int T_ = %s; (void)block_dimms; (void)thread_dimms;" % T,
-                 "    const int blocks_ = (T_ + SUGGESTED_THREADS - 1) / SUGGESTED_THREADS;",
+                 ("    const int blocks_ = T_ < 148*16 ? T_ : 148*16;   // one CTA per state, grid-stride beyond" if wide
+                  else "    const int blocks_ = (T_ + SUGGESTED_THREADS - 1) / SUGGESTED_THREADS;"),
                  "    const size_t smem_ = %s_DYNAMIC_SHARED_MEM_COUNT*sizeof(T);" % code]
         if not compute_only:
             lines += ["    " + c for c in copies_in] + ["    gpuErrchk(cudaDeviceSynchronize());"]
@@ -970,7 +1004,8 @@ class GRiDCodeGenerator:
                  "robot-specialised straight-line programs, one thread per state.  Compile with",
                  "nvcc -gencode arch=compute_100a,code=sm_100a.  Suggested (required) type T is float.",
                  "Kernels need dynamic shared memory <CODE>_DYNAMIC_SHARED_MEM_COUNT*sizeof(T), CODE in",
-                 "[ID, MINV, FD, ID_DU, FD_DU], and at most SUGGESTED_THREADS threads per block use it."]
+                 "[ID, MINV, FD, ID_DU, FD_DU], and at most SUGGESTED_THREADS threads per block use it.",
+                 "Kernel families in this file: " + ", ".join("%s=%s" % kv for kv in self._family.items())]
         self.gen_add_func_doc("This instance of %s.cuh is optimized for the urdf: %s" % (self.file_namespace,
                                                                                          self.robot.name), notes)
         self.gen_add_includes(use_thread_group)

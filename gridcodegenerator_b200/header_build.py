@@ -11,9 +11,12 @@ from .urdf import load_named_robot
 HARNESS_SRC = os.path.join(ROOT, "tests", "header_harness.cu")
 
 
-def build_header_harness(robot_name: str = "iiwa14", force: bool = False, device_fns: bool = True,
+def build_header_harness(robot_name: str = "iiwa14", force: bool = False, device_fns: bool = None,
                          timeout_s: int = 900) -> str:
     robot = load_named_robot(robot_name)
+    if device_fns is None:          # _inner/_device functions exist only where single-thread programs do
+        from .codegen import KernelPlan
+        device_fns = all("tps" in k for k in KernelPlan(robot).kind.values())
     h = hashlib.sha256((_static_hash() + robot.param_hash()).encode())
     for fn in (HARNESS_SRC, os.path.join(os.path.dirname(__file__), "facade.py")):
         with open(fn, "rb") as f:

@@ -112,20 +112,25 @@ def test_gen_all_code_writes_header_with_reference_contract(tmp_path, monkeypatc
         assert needle in text, needle
 
 
-def test_emitted_header_compiles_for_sm100a():
+@pytest.mark.parametrize("name", ["iiwa14", "atlas"])
+def test_emitted_header_compiles_for_sm100a(name):
     from gridcodegenerator_b200.header_build import build_header_harness
-    exe = build_header_harness("iiwa14")
+    exe = build_header_harness(name)
     assert os.path.exists(exe)
     out = subprocess.run(["cuobjdump", "-lelf", exe], capture_output=True, text=True).stdout
     assert "sm_100a" in out
 
 
 @pytest.mark.gpu
-def test_emitted_header_host_and_device_functions_on_gpu(tmp_path):
+@pytest.mark.parametrize("name,N", [("iiwa14", 200), ("atlas", 40)])
+def test_emitted_header_host_and_device_functions_on_gpu(tmp_path, name, N):
+    """iiwa14: every kernel is a thread-per-state program and the _inner/_device functions exist.
+    atlas: inverse dynamics is thread-per-state, the other four kernels are the wide CTA-per-state
+    kernels behind the same reference signatures (no _inner/_device functions)."""
     from gridcodegenerator_b200.header_build import build_header_harness
-    robot = load_named_robot("iiwa14")
-    n, N = robot.n, 200
-    exe = build_header_harness("iiwa14")
+    robot = load_named_robot(name)
+    n = robot.n
+    exe = build_header_harness(name)
     q, qd, u, qdd = make_states(n, N, 21)
     with open(tmp_path / "in.bin", "wb") as f:
         f.write(np.int32(N).tobytes())
@@ -144,7 +149,7 @@ def test_emitted_header_host_and_device_functions_on_gpu(tmp_path):
         return x
 
     q64, qd64, u64, qdd64 = (x.astype(np.float64) for x in (q, qd, u, qdd))
-    S = slice(0, 24)           # oracle sample
+    S = slice(0, 24 if name == "iiwa14" else 6)           # oracle sample
     ref_fd_grad = O.batch(robot, "fd_grad", q64[S], qd64[S], u64[S])
     assert relerr(take(n)[S], O.batch(robot, "id", q64[S], qd64[S])) < TOL["id"]
     assert relerr(take(n)[S], O.batch(robot, "id", q64[S], qd64[S], qdd64[S])) < TOL["id"]
@@ -156,6 +161,9 @@ def test_emitted_header_host_and_device_functions_on_gpu(tmp_path):
     assert relerr(df[S], ref_fd_grad) < TOL["fd_grad"]
     assert relerr(take(2 * n * n)[S], ref_fd_grad) < TOL["fd_grad"]          # USE_QDD_MINV_FLAG
     assert np.array_equal(take(2 * n * n), df)                                # _compute_only
+    if name != "iiwa14":
+        assert pos == data.size
+        return
     # device functions on state 0 (the last host call left FD's qdd in d_qdd)
     assert relerr(take(2 * n * n, 1)[0], ref_fd_grad[0]) < TOL["fd_grad"]    # forward_dynamics_gradient_device
     fdq = O.fd(robot, q64[0], qd64[0], u64[0])
