@@ -34,7 +34,10 @@ from .robot import Robot
 class SymRobot:
     """Per-state symbolic view of the robot: sin/cos of q and the X_i(q) actions."""
 
-    def __init__(self, p: Program, robot: Robot, q: Sequence[V]):
+    def __init__(self, p: Program, robot: Robot, q: Sequence[V], trig=None):
+        """trig = (sin list, cos list): take sin/cos of the revolute joints from the caller instead
+        of computing them from q (stage-B programs of pipeline.py import them from scratch memory);
+        q[i] is then only read for prismatic joints."""
         self.p, self.robot, self.n = p, robot, robot.n
         self.q = list(q)
         self.sin: List[Optional[V]] = []
@@ -44,8 +47,8 @@ class SymRobot:
             k = robot.S_ind[i]
             E0, r0 = robot.E0[i], robot.r0[i]
             if k < 3:
-                self.sin.append(p.sin(q[i]))
-                self.cos.append(p.cos(q[i]))
+                self.sin.append(trig[0][i] if trig is not None else p.sin(q[i]))
+                self.cos.append(trig[1][i] if trig is not None else p.cos(q[i]))
                 self.r.append([p.const(x) for x in r0])
             else:   # prismatic: r = r0 + q * E0[k-3, :]
                 self.sin.append(None)
@@ -251,13 +254,36 @@ def minv_get(Mi: Dict[Tuple[int, int], V], r: int, c: int) -> V:
 
 
 # ---- RNEA gradient -------------------------------------------------------------------
-def rnea_grad_columns(sr: SymRobot, qd: Sequence[V], R: RneaResult):
+class _DirectSource:
+    """Per-joint state data of the gradient columns taken straight from a traced RNEA."""
+
+    def __init__(self, p: Program, robot: Robot, R: RneaResult):
+        self.p, self.robot, self.R = p, robot, R
+
+    def v(self, i):
+        return self.R.v[i]
+
+    def Iv(self, i):
+        return self.R.Iv[i]
+
+    def mxs_Xa(self, i):
+        return cross_motion_axis(self.p, self.robot.S_ind[i], self.R.Xa[i])
+
+    def mxs_f(self, i):
+        return cross_motion_axis(self.p, self.robot.S_ind[i], self.R.f[i])
+
+
+def rnea_grad_columns(sr: SymRobot, qd: Sequence[V], R: Optional[RneaResult], src=None, joints=None):
     """Yields (j, dc_dq_col, dc_dqd_col) one du-column pair at a time; each col is a
     dict {row i: V} over anc(j) | sub(j) (structural zeros elsewhere).  Columns are
     independent through both passes, which is what lets the emitter finish and store
-    one column before starting the next."""
+    one column before starting the next.  `src` (default: the RNEA result itself) is where
+    the per-joint state data v, I v, mxS(X a_parent), mxS(f) come from; `joints` restricts
+    the columns (pipeline.py traces one group of columns per program)."""
     p, robot, n = sr.p, sr.robot, sr.n
-    for j in range(n):
+    if src is None:
+        src = _DirectSource(p, robot, R)
+    for j in (range(n) if joints is None else joints):
         kj = robot.S_ind[j]
         sub = robot.get_subtree_by_id(j)
         dv = {0: {}, 1: {}}
@@ -265,21 +291,22 @@ def rnea_grad_columns(sr: SymRobot, qd: Sequence[V], R: RneaResult):
         df = {0: {}, 1: {}}
         for i in sub:
             k = robot.S_ind[i]
+            vi, Ivi = src.v(i), src.Iv(i)
             if i == j:
-                dv[0][i] = cross_motion_axis(p, k, R.v[i])              # == mxS(X v_parent)
+                dv[0][i] = cross_motion_axis(p, k, vi)                  # == mxS(X v_parent)
                 e = zeros(p, 6)
                 e[k] = p.const(1.0)
                 dv[1][i] = e
-                da[0][i] = vadd(cross_motion_axis(p, k, dv[0][i], qd[i]), cross_motion_axis(p, k, R.Xa[i]))
-                da[1][i] = cross_motion_axis(p, k, R.v[i])
+                da[0][i] = vadd(cross_motion_axis(p, k, dv[0][i], qd[i]), src.mxs_Xa(i))
+                da[1][i] = cross_motion_axis(p, k, vi)
             else:
                 par = robot.parent[i]
                 for s in (0, 1):
                     dv[s][i] = sr.X_motion(i, dv[s][par])
                     da[s][i] = vadd(sr.X_motion(i, da[s][par]), cross_motion_axis(p, k, dv[s][i], qd[i]))
             for s in (0, 1):
-                df[s][i] = vadd(vadd(sr.I_mul(i, da[s][i]), cross_force(dv[s][i], R.Iv[i])),
-                                cross_force(R.v[i], sr.I_mul(i, dv[s][i])))
+                df[s][i] = vadd(vadd(sr.I_mul(i, da[s][i]), cross_force(dv[s][i], Ivi)),
+                                cross_force(vi, sr.I_mul(i, dv[s][i])))
         cols = ({}, {})
         for i in reversed(sub):
             par = robot.parent[i]
@@ -289,7 +316,7 @@ def rnea_grad_columns(sr: SymRobot, qd: Sequence[V], R: RneaResult):
                 for s in (0, 1):
                     df[s][par] = vadd(df[s][par], sr.XT_force(i, df[s][i]))
         # leave the subtree: the dq column also carries -X_j^T (f_j x) S_j
-        up = [vsub(df[0][j], cross_motion_axis(p, kj, R.f[j])), df[1][j]]
+        up = [vsub(df[0][j], src.mxs_f(j)), df[1][j]]
         i = j
         while robot.parent[i] >= 0:
             up = [sr.XT_force(i, up[0]), sr.XT_force(i, up[1])]

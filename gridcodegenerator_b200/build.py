@@ -25,7 +25,7 @@ GEN_DIR = os.path.join(PKG, "_generated")
 LIB_DIR = os.path.join(PKG, "_lib")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-gnu-unique", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-gnu-unique", "-shared", "-split-compile=0"]
 
 
 def _static_hash() -> str:
@@ -37,7 +37,7 @@ def _static_hash() -> str:
                 with open(os.path.join(d, fn), "rb") as f:
                     h.update(fn.encode())
                     h.update(f.read())
-    for fn in ("codegen.py", "algorithms.py", "ir.py"):
+    for fn in ("codegen.py", "algorithms.py", "ir.py", "pipeline.py"):
         with open(os.path.join(PKG, fn), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:10]

@@ -20,7 +20,7 @@ from .algorithms import TRACERS, algorithmic_flops
 from .ir import Program
 from .robot import Robot
 
-CODEGEN_VERSION = "1"
+CODEGEN_VERSION = "2"
 
 # variant -> (struct name, IN0 words / n, IN1 words / n, IN2 words / n^2, output array, OUT words as f(n))
 VARIANTS = {
@@ -509,7 +509,9 @@ class KernelPlan:
     def __init__(self, robot: Robot, tps_max_flops: int = 60000, tps_warps: int = 1,
                  tps_min_blocks: Optional[Dict[str, int]] = None, tps_sync_every: int = 0,
                  wps_max_states: int = 0, cps_max_states: int = 2048, tps_loop_columns: bool = False,
-                 tps_pairs: bool = False, tps_v2_park=None):
+                 tps_pairs: bool = False, tps_v2_park=None, pipe_algs=None, pipe_min_states: int = 0,
+                 pipe_opts: Optional[Dict[str, int]] = None, pipe_min_blocks: Tuple[int, int] = (1, 1),
+                 pipe_warps: int = 8):
         self.robot = robot
         self.tps_warps = tps_warps
         self.tps_sync_every = tps_sync_every if tps_warps > 1 else 0
@@ -530,8 +532,34 @@ class KernelPlan:
             # latency kernels: gradient algorithms of robots whose 2n columns fit one warp
             if tps and a in ("id_grad", "fd_grad") and 2 * robot.n <= 32:
                 self.kind[a] += "+cps"
+        # phase-split kernels (pipeline.py): by default for every algorithm that has no
+        # thread-per-state program; `pipe_algs` forces a set (experiments on small robots)
+        from .pipeline import PipeVariant, components
+        self.pipe_opts = dict(pipe_opts or {})
+        self.pipe_min_states = pipe_min_states
+        self.pipe_min_blocks = tuple(pipe_min_blocks)
+        self.pipe_warps = pipe_warps
+        self.pipe: Dict[str, "PipeVariant"] = {}
+        if pipe_algs is None:
+            # a forest of several trees: one thread per (state, tree) beats one thread per state
+            # (HyQ FD-gradient 2.25x, profiles/r1_matrix_pipe.jsonl); otherwise only where no
+            # thread-per-state program exists
+            forest = len(components(robot)) > 1
+            want = [a for a in self.kind if (forest and a != "id") or "tps" not in self.kind[a]]
+        else:
+            want = list(pipe_algs)
+        variants = {"id": ("id", "id_qdd"), "minv": ("minv",), "fd": ("fd",), "id_grad": ("id_grad", "id_grad_qdd"),
+                    "fd_grad": ("fd_grad",)}
+        for a in want:
+            pvs = [PipeVariant(robot, v, **self.pipe_opts) for v in variants[a]]
+            if all(pv.feasible for pv in pvs):
+                for pv in pvs:
+                    self.pipe[pv.variant] = pv
+                self.kind[a] = "pipe" if self.kind[a] == "none" else self.kind[a] + "+pipe"
         self.cps_lanes = 16 if 2 * robot.n <= 16 else 32
-        self.cps_max_states = cps_max_states
+        # with phase-split kernels available the latency kernels only win for small batches
+        # (HyQ FD gradient: cps 10.7 / 16.8 us vs pipe 10.8 / 12.8 us at N = 512 / 2048)
+        self.cps_max_states = min(cps_max_states, 512) if self.pipe else cps_max_states
         # resident single-warp CTAs per SM = register cap 65536/(32*min_blocks).  Measured on B200
         # (profiles/r1_sweep_tps.md): the gradient programs spill at 128/168 registers and run
         # 2.1x faster at 255 registers with no spills; the small programs fit 128.
@@ -570,6 +598,8 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
     # vague-linkage symbols (template statics) would otherwise be shared between them
     out.append("#define GRID_NS grid_%s_%s%s\n" % (re.sub(r"\W", "_", robot.name), robot.param_hash(), ns_tag))
     out.append('#include <cuda_runtime.h>\n#include "grid_tps.cuh"\n')
+    if plan.pipe:
+        out.append('#include "grid_pipe.cuh"\n')
     out.append('#define GRID_ROBOT_NAME "%s"\n#define GRID_ROBOT_HASH "%s"\n#define GRID_N %d\n'
                % (robot.name, robot.param_hash(), n))
     out.append("namespace GRID_NS { namespace gen {\n")
@@ -605,6 +635,12 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
             txt, cnt = emit_col_struct(robot, nm, alg, uq)
             out.append(txt)
             stats["cps_" + nm] = cnt
+    if plan.pipe:
+        from .pipeline import emit_pipe_struct
+        for v, pv in plan.pipe.items():
+            txt, summ = emit_pipe_struct(pv, plan.pipe_min_blocks, plan.pipe_warps)
+            out.append(txt)
+            stats["pipe_" + v] = summ
     out.append("}}  // namespace GRID_NS::gen\n")
     if has_cps:
         out.append('#include "grid_cps.cuh"\n')
@@ -620,12 +656,17 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
             return "tps2_launch<%s, %d, %d>" % (struct, W, plan.min_blocks[a])
         return "tps_launch<%s, %d, %d>" % (struct, W, plan.min_blocks[a])
 
-    def body(a, tps_call, wps_call, cps_call=()):
+    def body(a, tps_call, wps_call, cps_call=(), pipe_call=()):
         """tps_call / wps_call / cps_call: list of (condition or None, expression)."""
         lines = []
         if "cps" in plan.kind[a]:
             lines.append("    if (use_cps(N)) {")
             lines += ["        %sreturn %s;" % ("if (%s) " % c if c else "", e) for c, e in cps_call]
+            lines.append("    }")
+        if "pipe" in plan.kind[a]:
+            others = plan.kind[a] != "pipe"
+            lines.append("    if (%s) {" % ("use_pipe(N)" if others else "true"))
+            lines += ["        %sreturn %s;" % ("if (%s) " % c if c else "", e) for c, e in pipe_call]
             lines.append("    }")
         if has_tps(a) and has_wps(a):
             lines.append("    if (use_wide(N)) {")
@@ -653,19 +694,29 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
              "    const char *f = getenv(\"GRID_FORCE_KERNEL\");\n"
              "    if (f) return !strcmp(f, \"cps\");\n"
              "    return N <= %d;\n}" % plan.cps_max_states)
+    L.append("// large batches of robots with phase-split kernels (grid_pipe.cuh)\n"
+             "static bool use_pipe(int N) {\n"
+             "    const char *f = getenv(\"GRID_FORCE_KERNEL\");\n"
+             "    if (f) return !strcmp(f, \"pipe\");\n"
+             "    return N >= %d;\n}" % plan.pipe_min_states)
     G = plan.cps_lanes
+    PL = lambda struct, out, inp, in1: "pipe::pipe_launch<gen::%s>(%s, %s, stride, %s, N, g, s)" % (struct, out, inp, in1)
     L.append("cudaError_t launch_id(float *d_c, const float *d_q_qd, int stride, const float *d_qdd, int N, float g,"
              " cudaStream_t s) {")
     L += body("id", [("d_qdd", "%s(d_c, d_q_qd, stride, d_qdd, nullptr, N, g, s)" % tps("id", "AlgIdQdd")),
-                     (None, "%s(d_c, d_q_qd, stride, nullptr, nullptr, N, g, s)" % tps("id", "AlgId"))], [])
+                     (None, "%s(d_c, d_q_qd, stride, nullptr, nullptr, N, g, s)" % tps("id", "AlgId"))], [],
+              pipe_call=[("d_qdd", PL("PipeIdQdd", "d_c", "d_q_qd", "d_qdd")),
+                         (None, PL("PipeId", "d_c", "d_q_qd", "nullptr"))])
     L.append("}")
     L.append("cudaError_t launch_minv(float *d_Minv, const float *d_q, int stride, int N, cudaStream_t s) {")
     L += body("minv", [(None, "%s(d_Minv, d_q, stride, nullptr, nullptr, N, 0.f, s)" % tps("minv", "AlgMinv"))],
-              [(None, "wps::wps_launch<0, false>(d_Minv, d_q, stride, nullptr, nullptr, N, 0.f, s)")])
+              [(None, "wps::wps_launch<0, false>(d_Minv, d_q, stride, nullptr, nullptr, N, 0.f, s)")],
+              pipe_call=[(None, "pipe::pipe_launch<gen::PipeMinv>(d_Minv, d_q, stride, nullptr, N, 0.f, s)")])
     L.append("}")
     L.append("cudaError_t launch_fd(float *d_qdd, const float *d_q_qd_u, int stride, int N, float g, cudaStream_t s) {")
     L += body("fd", [(None, "%s(d_qdd, d_q_qd_u, stride, nullptr, nullptr, N, g, s)" % tps("fd", "AlgFd"))],
-              [(None, "wps::wps_launch<1, false>(d_qdd, d_q_qd_u, stride, nullptr, nullptr, N, g, s)")])
+              [(None, "wps::wps_launch<1, false>(d_qdd, d_q_qd_u, stride, nullptr, nullptr, N, g, s)")],
+              pipe_call=[(None, PL("PipeFd", "d_qdd", "d_q_qd_u", "nullptr"))])
     L.append("}")
     L.append("cudaError_t launch_id_grad(float *d_dc_du, const float *d_q_qd, int stride, const float *d_qdd, int N,"
              " float g, cudaStream_t s) {")
@@ -675,7 +726,9 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
               [("d_qdd", "wps::wps_launch<2, true>(d_dc_du, d_q_qd, stride, d_qdd, nullptr, N, g, s)"),
                (None, "wps::wps_launch<2, false>(d_dc_du, d_q_qd, stride, nullptr, nullptr, N, g, s)")],
               [("d_qdd", "cps_launch<gen::ColIdGradQdd, %d>(d_dc_du, d_q_qd, stride, d_qdd, N, g, s)" % G),
-               (None, "cps_launch<gen::ColIdGrad, %d>(d_dc_du, d_q_qd, stride, nullptr, N, g, s)" % G)])
+               (None, "cps_launch<gen::ColIdGrad, %d>(d_dc_du, d_q_qd, stride, nullptr, N, g, s)" % G)],
+              pipe_call=[("d_qdd", PL("PipeIdGradQdd", "d_dc_du", "d_q_qd", "d_qdd")),
+                         (None, PL("PipeIdGrad", "d_dc_du", "d_q_qd", "nullptr"))])
     L.append("}")
     L.append("cudaError_t launch_fd_grad(float *d_df_du, const float *d_in, int stride, const float *d_qdd,"
              " const float *d_Minv, int N, float g, cudaStream_t s) {")
@@ -684,12 +737,14 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
                (None, "%s(d_df_du, d_in, stride, nullptr, nullptr, N, g, s)" % tps("fd_grad", "AlgFdGrad"))],
               [("d_qdd", "wps::wps_launch<3, true>(d_df_du, d_in, stride, d_qdd, d_Minv, N, g, s)"),
                (None, "wps::wps_launch<3, false>(d_df_du, d_in, stride, nullptr, nullptr, N, g, s)")],
-              [("!d_qdd", "cps_launch<gen::ColFdGrad, %d>(d_df_du, d_in, stride, nullptr, N, g, s)" % G)])
+              [("!d_qdd", "cps_launch<gen::ColFdGrad, %d>(d_df_du, d_in, stride, nullptr, N, g, s)" % G)],
+              pipe_call=[("!d_qdd", PL("PipeFdGrad", "d_df_du", "d_in", "nullptr"))])
     L.append("}")
 
     kinds = "\n".join('    if (!strcmp(alg, "%s")) return "%s";' % (a, k) for a, k in plan.kind.items())
-    fl = "\n".join('    if (!strcmp(alg, "%s")) return %d;' % (a, stats[needed[a][0]]["flops"])
-                   for a in plan.kind if "tps" in plan.kind[a])
+    fl = "\n".join('    if (!strcmp(alg, "%s")) return %d;' % (
+        a, stats[needed[a][0]]["flops"] if "tps" in plan.kind[a] else plan.pipe[needed[a][0]].flops)
+        for a in plan.kind if "tps" in plan.kind[a] or "pipe" in plan.kind[a])
     out.append("#include <cstring>\n#include <cstdlib>\n")
     out.append(_LAUNCHERS % {"launchers": "\n".join(L), "kinds": kinds, "flops": fl})
     out.append('#include "grid_abi.cuh"\n')

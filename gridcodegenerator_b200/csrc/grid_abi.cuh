@@ -60,7 +60,14 @@ const char *grid_robot_hash(void) { return GRID_ROBOT_HASH; }
 const char *grid_last_error(void) { return GRID_NS::g_last_error.c_str(); }
 const char *grid_kernel_kind(const char *alg) { return GRID_NS::gen::kernel_kind(alg); }
 long long grid_traced_flops(const char *alg) { return GRID_NS::gen::traced_flops(alg); }
-long long grid_launch_count(void) { return GRID_NS::g_launches.load(); }
+/* kernels launched: a call served by the phase-split kernels launches one kernel per stage */
+long long grid_launch_count(void) {
+#ifdef GRID_HAS_PIPE
+    return GRID_NS::g_launches.load() + GRID_NS::pipe::g_kernel_launches.load() - GRID_NS::pipe::g_calls.load();
+#else
+    return GRID_NS::g_launches.load();
+#endif
+}
 
 #define GRID_LAUNCH(expr, name)                                         \
     do {                                                                \

@@ -1,0 +1,505 @@
+"""Phase-split ("pipe") kernels: traced straight-line programs for robots whose whole
+algorithm does not fit one thread.
+
+The thread-per-state kernels (csrc/grid_tps.cuh) run one traced program per state.  That
+stops working when the program outgrows 255 registers (Atlas FD-gradient: 72 k traced flops,
+47 KB of spill traffic per state).  Two structural facts of the reference algorithms give a
+decomposition into programs that DO fit:
+
+  * **Forest components.**  Joints whose root ancestors differ never interact on a fixed
+    base: M is block-diagonal, c_i only depends on its own component (the reference's
+    ancestor/subtree tests, helpers/_topology_helpers.py:193-215, already encode this as
+    structural zeros).  Atlas = {torso+arms+neck (18), left leg (6), right leg (6)}, HyQ =
+    4 legs of 3.  One thread runs one (state, component).
+  * **Column independence of the gradient.**  Every du-column of dc_du runs its own
+    forward/backward recursion (algorithms/_inverse_dynamics_gradient.py:189-541 loops over
+    columns inside every wave; oracle _test.py:229-488); the only shared data are the RNEA
+    results v, I v, mxS(X a_parent), mxS(f) and, for the FD gradient, Minv
+    (algorithms/_forward_dynamics_gradient.py:48-57).  Stage A (one thread per state and
+    component) computes those once and writes them to a scratch array; stage B (one thread
+    per state and GROUP of columns) reads them back and finishes its columns.
+
+Scratch layout: [tile of 32 states][word][lane] - every access of a warp is one 128-byte
+line, word offsets are compile-time immediates.  Output columns are staged per warp in shared
+memory and flushed as runs of n contiguous floats per state.
+
+A Program traced here names its inputs "in:<w>" (word w of the state's input row
+[in0 | in1]), "sc:<key>" (scratch, key resolved to a word by PipeVariant) and "gravity";
+outputs are ("sc", word) and ("out", flat index in the state's output row).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+from .algorithms import (RneaResult, SymRobot, cross_motion_axis, minv, minv_get, rnea,
+                         rnea_grad_columns)
+from .ir import Program, V, dot
+from .robot import Robot
+
+# variant -> (struct name, IN0 / n, IN1 / n, OUT as f(n))
+PIPE_VARIANTS = {
+    "id":          ("PipeId",         2, 0, lambda n: n),
+    "id_qdd":      ("PipeIdQdd",      2, 1, lambda n: n),
+    "minv":        ("PipeMinv",       1, 0, lambda n: n * n),
+    "fd":          ("PipeFd",         3, 0, lambda n: n),
+    "id_grad":     ("PipeIdGrad",     2, 0, lambda n: 2 * n * n),
+    "id_grad_qdd": ("PipeIdGradQdd",  2, 1, lambda n: 2 * n * n),
+    "fd_grad":     ("PipeFdGrad",     3, 0, lambda n: 2 * n * n),
+}
+
+
+def components(robot: Robot) -> List[List[int]]:
+    """Joint ids of each tree hanging off the base (contiguous ranges: ids are a DFS pre-order)."""
+    out = []
+    for i in range(robot.n):
+        if robot.parent[i] < 0:
+            out.append(robot.get_subtree_by_id(i))
+    return out
+
+
+def subrobot(robot: Robot, ids: Sequence[int], name: Optional[str] = None) -> Robot:
+    m = {g: l for l, g in enumerate(ids)}
+    return Robot(name or "%s_%d_%d" % (robot.name, ids[0], ids[-1]),
+                 [m.get(robot.parent[g], -1) for g in ids], [robot.S_ind[g] for g in ids],
+                 [robot.E0[g].copy() for g in ids], [robot.r0[g].copy() for g in ids],
+                 [robot.Imats[g].copy() for g in ids], [robot.damping[g] for g in ids])
+
+
+class PipeTask:
+    """One traced program = one thread per (state, task)."""
+
+    def __init__(self, name: str, stage: int, program: Program, runs: List[Tuple[Tuple[int, ...], int]]):
+        self.name, self.stage, self.program, self.runs = name, stage, program, runs
+        self.counts = program.op_counts()
+
+    @property
+    def flops(self) -> int:
+        return self.counts["flops"]
+
+
+# ---- stage A: per-component state programs ---------------------------------------------------
+class _Exports:
+    """Values stage A can hand to stage B, by name.  Constants (structural zeros of the root
+    joints, ...) are folded into the importing program instead of being stored."""
+
+    def __init__(self):
+        self.cand: Dict[str, V] = {}
+
+    def add(self, name: str, v: V):
+        self.cand[name] = v
+
+    def importer(self, p: Program):
+        def imp(name: str) -> V:
+            v = self.cand[name]
+            if v.is_const:
+                return p.const(v.c)
+            x = p.inp("sc:%d" % v.i)          # keyed by the producing node: aliases share a word
+            return x if v.s > 0 else -x
+        return imp
+
+
+def _state_inputs(p: Program, n: int, ids: Sequence[int], block: int) -> List[V]:
+    return [p.inp("in:%d" % (block * n + g)) for g in ids]
+
+
+def _trace_stage_a(robot: Robot, ids: Sequence[int], alg: str, use_qdd: bool):
+    sub, n = subrobot(robot, ids), robot.n
+    nc = sub.n
+    p = Program()
+    q, qd = _state_inputs(p, n, ids, 0), _state_inputs(p, n, ids, 1)
+    g = p.inp("gravity")
+    S = SymRobot(p, sub, q)
+    Mi = None
+    if alg == "fd_grad":
+        u = _state_inputs(p, n, ids, 2)
+        R0 = rnea(S, qd, None, g)
+        Mi = minv(S)
+        umc = [u[i] - R0.c[i] for i in range(nc)]
+        qdd = [dot([minv_get(Mi, i, j) for j in range(nc)], umc) for i in range(nc)]
+    else:
+        qdd = _state_inputs(p, n, ids, 2) if use_qdd else None      # in1 follows the 2n words of in0
+    R = rnea(S, qd, qdd, g)
+    ex = _Exports()
+    for i in range(nc):
+        k = sub.S_ind[i]
+        if k < 3:
+            ex.add("sin%d" % i, S.sin[i])
+            ex.add("cos%d" % i, S.cos[i])
+        else:
+            ex.add("q%d" % i, q[i])
+        ex.add("qd%d" % i, qd[i])
+        mXa = cross_motion_axis(p, k, R.Xa[i])
+        mf = cross_motion_axis(p, k, R.f[i])
+        for r in range(6):
+            ex.add("v%d_%d" % (i, r), R.v[i][r])
+            ex.add("Iv%d_%d" % (i, r), R.Iv[i][r])
+            ex.add("mXa%d_%d" % (i, r), mXa[r])
+            ex.add("mf%d_%d" % (i, r), mf[r])
+    if Mi is not None:
+        for (r, c), v in Mi.items():
+            ex.add("M%d_%d" % (r, c), v)
+    return p, ex, sub
+
+
+class _ImportSource:
+    def __init__(self, imp):
+        self.imp = imp
+
+    def _six(self, nm, i):
+        return [self.imp("%s%d_%d" % (nm, i, r)) for r in range(6)]
+
+    def v(self, i):
+        return self._six("v", i)
+
+    def Iv(self, i):
+        return self._six("Iv", i)
+
+    def mxs_Xa(self, i):
+        return self._six("mXa", i)
+
+    def mxs_f(self, i):
+        return self._six("mf", i)
+
+
+def _column_outputs(p: Program, n: int, ids: Sequence[int], j: int, cq, cqd, M):
+    """Writes the two full output columns of local joint j (zeros outside the component)."""
+    nc, base, jg = len(ids), ids[0], ids[j]
+    for s, col in ((0, cq), (1, cqd)):
+        if M is None:
+            vals = col
+        else:
+            rows = sorted(col)
+            vals = {i: -dot([M(i, r) for r in rows], [col[r] for r in rows]) for i in range(nc)}
+        for ig in range(n):
+            l = ig - base
+            p.output("out", s * n * n + n * jg + ig, vals.get(l, 0.0) if 0 <= l < nc else 0.0)
+    return ((n * jg, n * n + n * jg), n)
+
+
+def _trace_stage_b(robot: Robot, ids: Sequence[int], sub: Robot, joints: Sequence[int], alg: str, ex: _Exports):
+    n, nc = robot.n, sub.n
+    p = Program()
+    imp = ex.importer(p)
+    rev = [sub.S_ind[i] < 3 for i in range(nc)]
+    sin = [imp("sin%d" % i) if rev[i] else None for i in range(nc)]
+    cos = [imp("cos%d" % i) if rev[i] else None for i in range(nc)]
+    q = [None if rev[i] else imp("q%d" % i) for i in range(nc)]
+    S = SymRobot(p, sub, q, trig=(sin, cos))
+    qd = [imp("qd%d" % i) for i in range(nc)]
+    M = (lambda r, c: imp("M%d_%d" % (min(r, c), max(r, c)))) if alg == "fd_grad" else None
+    runs = []
+    for j, cq, cqd in rnea_grad_columns(S, qd, None, src=_ImportSource(imp), joints=joints):
+        runs.append(_column_outputs(p, n, ids, j, cq, cqd, M))
+    return p, runs
+
+
+# ---- single-stage programs: one (state, component) per thread -----------------------------------
+def _trace_full(robot: Robot, ids: Sequence[int], alg: str, use_qdd: bool):
+    sub, n = subrobot(robot, ids), robot.n
+    nc, base = sub.n, ids[0]
+    p = Program()
+    q = _state_inputs(p, n, ids, 0)
+    S = SymRobot(p, sub, q)
+    runs: List[Tuple[Tuple[int, ...], int]] = []
+    if alg == "minv":
+        Mi = minv(S)
+        for j in range(nc):
+            jg = ids[j]
+            for ig in range(n):
+                l = ig - base
+                p.output("out", jg * n + ig, Mi[(l, j)] if 0 <= l <= j else 0.0)
+            runs.append(((jg * n,), n))
+        return p, runs
+    qd = _state_inputs(p, n, ids, 1)
+    g = p.inp("gravity")
+    if alg == "id":
+        qdd = _state_inputs(p, n, ids, 2) if use_qdd else None
+        R = rnea(S, qd, qdd, g)
+        for i in range(nc):
+            p.output("out", ids[i], R.c[i])
+        return p, [((base,), nc)]
+    if alg == "fd":
+        u = _state_inputs(p, n, ids, 2)
+        R = rnea(S, qd, None, g)
+        Mi = minv(S)
+        umc = [u[i] - R.c[i] for i in range(nc)]
+        for i in range(nc):
+            p.output("out", ids[i], dot([minv_get(Mi, i, j) for j in range(nc)], umc))
+        return p, [((base,), nc)]
+    M = None
+    if alg == "fd_grad":
+        u = _state_inputs(p, n, ids, 2)
+        R0 = rnea(S, qd, None, g)
+        Mi = minv(S)
+        umc = [u[i] - R0.c[i] for i in range(nc)]
+        qdd = [dot([minv_get(Mi, i, j) for j in range(nc)], umc) for i in range(nc)]
+        M = lambda r, c: minv_get(Mi, r, c)
+    else:
+        qdd = _state_inputs(p, n, ids, 2) if use_qdd else None
+    R = rnea(S, qd, qdd, g)
+    for j, cq, cqd in rnea_grad_columns(S, qd, R):
+        runs.append(_column_outputs(p, n, ids, j, cq, cqd, M))
+    return p, runs
+
+
+class PipeVariant:
+    """All tasks of one algorithm variant of one robot, plus its scratch layout."""
+
+    def __init__(self, robot: Robot, variant: str, single_stage_max_flops: int = 12000,
+                 group_flops: int = 6500, stage_a_max_flops: int = 20000):
+        self.robot, self.variant = robot, variant
+        sname, m0, m1, out_fn = PIPE_VARIANTS[variant]
+        n = robot.n
+        self.struct = sname
+        self.in0, self.in1, self.out = m0 * n, m1 * n, out_fn(n)
+        alg = {"id_qdd": "id", "id_grad_qdd": "id_grad"}.get(variant, variant)
+        use_qdd = variant.endswith("_qdd")
+        self.tasks: List[PipeTask] = []
+        self.scratch_words = 0
+        self.feasible = True
+        sc_base = 0
+        for ci, ids in enumerate(components(robot)):
+            pf, runs = _trace_full(robot, ids, alg, use_qdd)
+            full = PipeTask("c%d_full" % ci, 0, pf, runs)
+            if alg not in ("id_grad", "fd_grad") or full.flops <= single_stage_max_flops:
+                if full.flops > stage_a_max_flops:
+                    self.feasible = False
+                self.tasks.append(full)
+                continue
+            # two stages: A = state program, B = groups of du-columns
+            pa, ex, sub = _trace_stage_a(robot, ids, alg, use_qdd)
+            nc = sub.n
+            # cost of every single column pair, then greedy packing of contiguous joints
+            cost = []
+            for j in range(nc):
+                pb, _ = _trace_stage_b(robot, ids, sub, [j], alg, ex)
+                cost.append(pb.op_counts()["flops"])
+            groups, cur, acc = [], [], 0
+            for j in range(nc):
+                if cur and acc + cost[j] > group_flops:
+                    groups.append(cur)
+                    cur, acc = [], 0
+                cur.append(j)
+                acc += cost[j]
+            if cur:
+                groups.append(cur)
+            btasks = []
+            used: Dict[int, None] = {}
+            for gi, J in enumerate(groups):
+                pb, runs = _trace_stage_b(robot, ids, sub, J, alg, ex)
+                live = pb.live_nodes()
+                for i, k in enumerate(pb.nodes):
+                    if live[i] and k[0] == "in" and k[1].startswith("sc:"):
+                        used[int(k[1][3:])] = None
+                btasks.append((gi, J, pb, runs))
+            # scratch words in stage-A production order
+            word_of = {node: sc_base + w for w, node in enumerate(sorted(used))}
+            sc_base += len(word_of)
+            for node, w in word_of.items():
+                pa.output("sc", w, V(pa, i=node))
+            ta = PipeTask("c%d_A" % ci, 0, pa, [])
+            if ta.flops > stage_a_max_flops:
+                self.feasible = False
+            self.tasks.append(ta)
+            for gi, J, pb, runs in btasks:
+                t = PipeTask("c%d_B%d_j%d_%d" % (ci, gi, ids[J[0]], ids[J[-1]]), 1, pb, runs)
+                if t.flops > stage_a_max_flops:          # a single column too long for one thread (64-link chain)
+                    self.feasible = False
+                t.sc_word = {("sc:%d" % node): w for node, w in word_of.items()}
+                self.tasks.append(t)
+        self.scratch_words = sc_base
+        # heavy tasks first: CTAs are dispatched in blockIdx order
+        self.stage_tasks = [sorted([t for t in self.tasks if t.stage == s], key=lambda t: -t.flops) for s in (0, 1)]
+        self.flops = sum(t.flops for t in self.tasks)
+
+    def evaluate(self, in_rows, gravity: float = 9.81, dtype=None):
+        """Interprets the task programs with numpy in kernel order (stage 0, then stage 1) - the
+        host-side check of the decomposition (tests/test_pipeline.py); never a product path.
+        in_rows: (N, IN0 + IN1) array; returns (N, OUT) with NaN in words no task wrote."""
+        import numpy as np
+        dtype = dtype or np.float64
+        rows = np.asarray(in_rows, dtype=dtype)
+        N = rows.shape[0]
+        out = np.full((N, self.out), np.nan, dtype=dtype)
+        scratch = np.full((N, max(1, self.scratch_words)), np.nan, dtype=dtype)
+        for stage in (0, 1):
+            for t in self.stage_tasks[stage]:
+                inputs = {}
+                for name in t.program.inputs:
+                    if name == "gravity":
+                        inputs[name] = dtype(gravity)
+                    elif name.startswith("in:"):
+                        inputs[name] = rows[:, int(name[3:])]
+                    else:
+                        inputs[name] = scratch[:, t.sc_word[name]] if name in getattr(t, "sc_word", {}) else np.nan
+                res = t.program.evaluate(inputs, dtype=dtype)
+                for name, idx, _ in t.program.outputs:
+                    (scratch if name == "sc" else out)[:, idx] = res[name][:, idx]
+        return out
+
+    def summary(self) -> Dict[str, object]:
+        return {"flops": self.flops, "scratch_words": self.scratch_words,
+                "tasks": [(t.name, t.stage, t.flops) for st in self.stage_tasks for t in st]}
+
+
+# ---- emission ----------------------------------------------------------------------------------
+def _flit(x: float) -> str:
+    s = "%.9g" % x
+    if "e" not in s and "." not in s and "inf" not in s and "nan" not in s:
+        s += ".0"
+    return s + "f"
+
+
+def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead: int = 24,
+              scratch_lead: int = 160, indent: str = "        ") -> List[str]:
+    """One task as a __device__ function.  Input loads are issued `lead` operations before
+    their first use (long enough to cover the L2 latency of scratch reads, short enough not to
+    pin registers); output runs are flushed as soon as their last value exists."""
+    p = t.program
+    live = p.live_nodes()
+    sc_word = getattr(t, "sc_word", {})
+    order = [i for i, k in enumerate(p.nodes) if live[i] and k[0] != "in"]
+    pos = {i: c for c, i in enumerate(order)}
+    first_use: Dict[int, int] = {}
+    for i in order:
+        for o in p.operands(i):
+            if p.nodes[o][0] == "in" and o not in first_use:
+                first_use[o] = pos[i]
+    out_pos: Dict[int, List[Tuple[str, int, V]]] = {}
+    for (name, idx, v) in p.outputs:
+        if not v.is_const and p.nodes[v.i][0] == "in":
+            first_use.setdefault(v.i, 0)
+    loads_at: Dict[int, List[str]] = {}
+    load_pos: Dict[int, int] = {}
+    for o, fu in first_use.items():
+        name = p.nodes[o][1]
+        if name == "gravity":
+            stmt, lead = "const float t%d = gravity;" % o, 0
+        elif name.startswith("in:"):
+            stmt, lead = "const float t%d = s_in[%d];" % (o, int(name[3:])), tile_lead
+        else:
+            stmt, lead = "const float t%d = __ldg(sc_in + %d);" % (o, 32 * sc_word[name]), scratch_lead
+        load_pos[o] = max(0, fu - lead)
+        loads_at.setdefault(load_pos[o], []).append(indent + stmt)
+
+    # outputs: scratch words are stored where produced; "out" words wait for their run
+    run_of: Dict[int, int] = {}
+    for ri, (offs, ln) in enumerate(t.runs):
+        for si, off in enumerate(offs):
+            for c in range(ln):
+                run_of[off + c] = ri
+    run_vals: List[Dict[int, V]] = [dict() for _ in t.runs]
+    run_last = [-1] * len(t.runs)
+    sc_at: Dict[int, List[str]] = {}
+    for (name, idx, v) in p.outputs:
+        # constants go first; a passed-through input follows its own load
+        where = -1 if v.is_const else (load_pos[v.i] if p.nodes[v.i][0] == "in" else pos[v.i])
+        if name == "sc":
+            expr = _flit(v.c) if v.is_const else "%st%d" % ("-" if v.s < 0 else "", v.i)
+            sc_at.setdefault(where, []).append("%ssc_out[%d] = %s;" % (indent, 32 * idx, expr))
+        else:
+            ri = run_of[idx]
+            if idx in run_vals[ri]:
+                raise ValueError("output word %d written twice" % idx)
+            run_vals[ri][idx] = v
+            run_last[ri] = max(run_last[ri], where)
+    flush_at: Dict[int, List[int]] = {}
+    for ri, (offs, ln) in enumerate(t.runs):
+        if len(run_vals[ri]) != ln * len(offs):
+            raise ValueError("task %s does not cover run %d" % (t.name, ri))
+        flush_at.setdefault(run_last[ri], []).append(ri)
+
+    def flush(ri: int) -> List[str]:
+        offs, ln = t.runs[ri]
+        L = []
+        for si, off in enumerate(offs):
+            for c in range(ln):
+                v = run_vals[ri][off + c]
+                expr = _flit(v.c) if v.is_const else "%st%d" % ("-" if v.s < 0 else "", v.i)
+                L.append("%ss_stage[%d] = %s;" % (indent, si * ln + c, expr))
+        L.append("%s__syncwarp();" % indent)
+        if len(offs) == 1:
+            L.append("%spipe::flush1<%d, %d, %d>(g_tile, s_warp, %d, cnt, lane);" % (indent, out_words, ln, stage_pad, offs[0]))
+        else:
+            L.append("%spipe::flush2<%d, %d, %d>(g_tile, s_warp, %d, %d, cnt, lane);" % (
+                indent, out_words, ln, stage_pad, offs[0], offs[1]))
+        L.append("%s__syncwarp();" % indent)
+        return L
+
+    body: List[str] = ["    // %s: %d mul + %d add per state" % (t.name, t.counts["mul"], t.counts["add"]),
+                       "    static __device__ __noinline__ void %s(const float *s_in, const float *__restrict__ sc_in,"
+                       " float *__restrict__ sc_out, float *s_stage, float *__restrict__ g_tile, const int cnt,"
+                       " const int lane, const float *s_warp, const float gravity) {" % fname]
+    body += sc_at.get(-1, [])
+    for ri in flush_at.get(-1, []):
+        body += flush(ri)
+    sincos_done = set()
+    for c in range(max(1, len(order))):
+        body += loads_at.get(c, [])
+        i = order[c] if c < len(order) else None
+        k = p.nodes[i] if i is not None else ("nop",)
+        op = k[0]
+        if op == "nop":
+            pass
+        elif op in ("sin", "cos"):
+            a = k[1]
+            if a not in sincos_done:
+                sincos_done.add(a)
+                si, ci = p._cse.get(("sin", a)), p._cse.get(("cos", a))
+                sn = "t%d" % si if si is not None and live[si] else "unused_s%d" % a
+                cn = "t%d" % ci if ci is not None and live[ci] else "unused_c%d" % a
+                body.append("%sfloat %s, %s; sincosf(t%d, &%s, &%s);" % (indent, sn, cn, a, sn, cn))
+        elif op == "rcp":
+            body.append("%sconst float t%d = 1.0f / t%d;" % (indent, i, k[1]))
+        elif op == "mul":
+            body.append("%sconst float t%d = t%d * t%d;" % (indent, i, k[1], k[2]))
+        elif op == "mulc":
+            body.append("%sconst float t%d = t%d * %s;" % (indent, i, k[1], _flit(k[2])))
+        elif op == "add":
+            body.append("%sconst float t%d = t%d %s t%d;" % (indent, i, k[1], "+" if k[3] > 0 else "-", k[2]))
+        elif op == "addc":
+            body.append("%sconst float t%d = t%d + %s;" % (indent, i, k[1], _flit(k[2])))
+        else:
+            raise ValueError("pipe emitter: unsupported node %r" % (k,))
+        body += sc_at.get(c, [])
+        for ri in flush_at.get(c, []):
+            body += flush(ri)
+    body.append("    }")
+    return body
+
+
+def emit_pipe_struct(pv: PipeVariant, min_blocks: Tuple[int, int] = (1, 1), warps: int = 8) -> Tuple[str, Dict[str, object]]:
+    """min_blocks: resident CTAs per SM the two stage kernels are compiled for (register cap =
+    65536 / (32 * warps * min_blocks)); warps: tiles (warps) per CTA."""
+    max_run = max([len(offs) * ln for t in pv.tasks for (offs, ln) in t.runs] + [1])
+    # row pitch of the staging tile: even (float2 flushes) when every run length is even, else odd
+    # (conflict-free scalar access); never a multiple of 32
+    if all(ln % 2 == 0 for t in pv.tasks for (_, ln) in t.runs):
+        stage_pad = max_run + (2 if max_run % 32 == 0 else 0)
+    else:
+        stage_pad = max_run | 1
+    txt = ["struct %s {" % pv.struct,
+           "    static constexpr int IN0 = %d, IN1 = %d, OUT = %d, SCRATCH_WORDS = %d, STAGE_PAD = %d;" % (
+               pv.in0, pv.in1, pv.out, pv.scratch_words, stage_pad),
+           "    static constexpr int NTASKS0 = %d, NTASKS1 = %d, MINB0 = %d, MINB1 = %d, WARPS = %d;" % (
+               len(pv.stage_tasks[0]), len(pv.stage_tasks[1]), min_blocks[0], min_blocks[1], warps),
+           "    static constexpr long long TRACED_FLOPS = %d;" % pv.flops]
+    for s in (0, 1):
+        for ti, t in enumerate(pv.stage_tasks[s]):
+            txt += emit_task(t, "s%d_t%d" % (s, ti), pv.out, stage_pad)
+    txt.append("    template <int STAGE> static __device__ __forceinline__ void run(const int task, const float *s_in,"
+               " const float *__restrict__ sc_in, float *__restrict__ sc_out, float *s_stage,"
+               " float *__restrict__ g_tile, const int cnt, const int lane, const float *s_warp, const float gravity) {")
+    for s in (0, 1):
+        if not pv.stage_tasks[s]:
+            continue
+        txt.append("        if (STAGE == %d) {" % s)
+        txt.append("            switch (task) {")
+        for ti in range(len(pv.stage_tasks[s])):
+            txt.append("            case %d: s%d_t%d(s_in, sc_in, sc_out, s_stage, g_tile, cnt, lane, s_warp, gravity); break;"
+                       % (ti, s, ti))
+        txt.append("            default: break;")
+        txt.append("            }")
+        txt.append("        }")
+    txt += ["    }", "};", ""]
+    return "\n".join(txt), pv.summary()

@@ -16,7 +16,7 @@ from gridcodegenerator_b200.synthetic import make_states, pack_q_qd, pack_q_qd_u
 from oracle import rbd_numpy as O                                       # noqa: E402
 
 ALL = ("id", "minv", "fd", "id_grad", "fd_grad")
-FAMILIES = ("tps", "wps", "cps")
+FAMILIES = ("tps", "wps", "cps", "pipe")
 
 
 class forced:
@@ -218,7 +218,32 @@ def test_full_batches_against_c_oracle(name, N, algs):
         assert per.max() < 50 * TOL[alg], (name, alg, per.max())
 
 
-@pytest.mark.parametrize("name,family", [("atlas", "wps"), ("iiwa14", "tps"), ("iiwa14", "cps"), ("mixed5", "wps")])
+@pytest.mark.parametrize("alg", ["minv", "fd", "id_grad", "fd_grad"])
+@pytest.mark.parametrize("N", [1, 31, 33, 1000])
+def test_pipe_ragged_batches_atlas(N, alg, monkeypatch):
+    """Phase-split kernels: ragged last tile, guard rows around the output, same values for any
+    batch size, and the scratch words of lanes past the end never reach the output."""
+    monkeypatch.setenv("GRID_FORCE_KERNEL", "pipe")
+    robot = load_named_robot("atlas")
+    eng = get_engine(robot)
+    assert "pipe" in eng.kernel_kind(alg)
+    n = robot.n
+    q, qd, u, _ = make_states(n, 1000, 5)
+    big = run_alg(eng, alg, q, qd, u)
+    words = big.shape[1]
+    guard = torch.full((N + 2, words), 7.0, device="cuda")
+    x = dev(pack_q_qd_u(q[:N], qd[:N], u[:N]))
+    call = {"minv": eng.direct_minv_device, "fd": eng.forward_dynamics_device,
+            "id_grad": eng.inverse_dynamics_gradient_device, "fd_grad": eng.forward_dynamics_gradient_device}[alg]
+    call(guard[1:N + 1], x, num_timesteps=N, stride=3 * n)
+    torch.cuda.synchronize()
+    g = guard.cpu().numpy()
+    assert np.all(g[0] == 7.0) and np.all(g[-1] == 7.0)
+    assert np.array_equal(g[1:N + 1], big[:N])
+
+
+@pytest.mark.parametrize("name,family", [("atlas", "wps"), ("atlas", "pipe"), ("iiwa14", "tps"), ("iiwa14", "cps"),
+                                         ("mixed5", "wps")])
 def test_repeated_launches_are_bit_identical(name, family, monkeypatch):
     """compute-sanitizer is closed on this pool, so races are hunted the indirect way: the wide
     kernels use named barriers, aliased scratch and shared-memory atomics - any race would show up as

@@ -1,6 +1,9 @@
 #!/usr/bin/env python3
 """Times (robot, algorithm, batch, kernel family) combinations with CUDA events; JSON lines out.
   python tools/bench_matrix.py iiwa14:fd_grad:128:wps iiwa14:fd_grad:128:tps atlas:fd_grad:65536:auto ...
+A robot name may carry a library tag (iiwa14@_pipe16: an experimental build made beforehand with
+build_robot_library(..., tag="_pipe16")).  Every line also reports the FP32 error of the first
+states against the float64 C oracle.
 """
 import json
 import os
@@ -15,20 +18,22 @@ from gridcodegenerator_b200 import load_named_robot                      # noqa:
 from gridcodegenerator_b200.algorithms import algorithmic_flops         # noqa: E402
 from gridcodegenerator_b200.runtime import get_engine                    # noqa: E402
 from gridcodegenerator_b200.synthetic import make_states, pack_q_qd_u    # noqa: E402
+from oracle import c_oracle as C                                         # noqa: E402
 
 
 def main():
     for spec in sys.argv[1:]:
         name, alg, N, family = spec.split(":")
+        name, _, tag = name.partition("@")
         N = int(N)
         robot = load_named_robot(name)
-        eng = get_engine(robot)
+        eng = get_engine(robot, tag=tag)
         n = robot.n
-        if family in ("tps", "wps"):
+        if family in ("tps", "wps", "cps", "pipe"):
             os.environ["GRID_FORCE_KERNEL"] = family
         else:
             os.environ.pop("GRID_FORCE_KERNEL", None)
-        if family in ("tps", "wps") and family not in eng.kernel_kind(alg):
+        if family in ("tps", "wps", "cps", "pipe") and family not in eng.kernel_kind(alg):
             print(json.dumps({"spec": spec, "skipped": "no %s kernel" % family}), flush=True)
             continue
         q, qd, u, _ = make_states(n, N, 3)
@@ -44,8 +49,13 @@ def main():
         us = eng.time_launches(alg, out, x, reps=reps)      # event pairs recorded in C, launches queued back to back
         p50 = float(np.median(us))
         fl = algorithmic_flops(robot)[alg]
+        M = min(N, 2048)
+        q64, qd64, u64 = (a[:M].astype(np.float64) for a in (q, qd, u))
+        ref = C.batch(robot, alg, q64, qd64, u64 if alg in ("fd", "fd_grad") else None)
+        o = out[:M].cpu().numpy().astype(np.float64)
         print(json.dumps({"spec": spec, "p50_us": p50, "min_us": float(us.min()), "evals_per_s": N / p50 * 1e6,
-                          "alg_tflops": fl * N / p50 / 1e6}), flush=True)
+                          "alg_tflops": fl * N / p50 / 1e6,
+                          "rel_err": float(np.abs(o - ref).max() / np.abs(ref).max())}), flush=True)
 
 
 if __name__ == "__main__":
