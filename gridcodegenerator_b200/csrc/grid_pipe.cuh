@@ -15,6 +15,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <cstdlib>
+#include <cstring>
 #include "grid_tps.cuh"
 #define GRID_HAS_PIPE 1
 
@@ -23,28 +25,66 @@ namespace GRID_NS { namespace pipe {
 static std::atomic<long long> g_kernel_launches{0};     // kernels launched (an ABI call launches one per stage)
 static std::atomic<long long> g_calls{0};
 
+// Scratch words are written and read inside one kernel (by different SMs) in the fused kernel, so
+// they must not go through the non-coherent path: ld.global.cg reads them at L2.
+__device__ __forceinline__ float ldsc(const float *p) { return __ldcg(p); }
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // Flush of one or two runs of LEN contiguous output words per state from the warp's staging rows
-// (row pitch PAD).  Element e of the tile is (state e / W, word e % W); lane handles e = lane,
-// lane + 32, ... so consecutive lanes store consecutive words.  (s, c) are advanced incrementally
-// (no division in the loop); even LEN / PAD / offsets move float2.
+// (row pitch PAD).  Each lane owns one (float or float2) word position c of the run pair and, when
+// the pair is short, one of K = 32 / Wp states per step: all index arithmetic is hoisted out of the
+// loop, whose body is one shared load, one global store and one predicate with immediate offsets
+// (the element-wise mapping it replaces cost 9 instructions per word: 19 % of the iiwa14 kernel).
+// predicated global store without a branch: `if (k < left) *p = v`
+__device__ __forceinline__ void st_if_lt(float *p, float v, int k, int left) {
+    asm volatile("{ .reg .pred q; setp.lt.s32 q, %2, %3; @q st.global.f32 [%0], %1; }" ::"l"(p), "f"(v), "r"(k), "r"(left)
+                 : "memory");
+}
+__device__ __forceinline__ void st_if_lt(float2 *p, float2 v, int k, int left) {
+    asm volatile("{ .reg .pred q; setp.lt.s32 q, %3, %4; @q st.global.v2.f32 [%0], {%1, %2}; }" ::"l"(p), "f"(v.x),
+                 "f"(v.y), "r"(k), "r"(left)
+                 : "memory");
+}
+
+template <typename T, int OUT, int LEN, int PAD, int NRUN>      // OUT, LEN, PAD, offsets in units of T
+__device__ __forceinline__ void flush_rows(T *__restrict__ g_tile, const T *s_warp, int off0, int off1, int cnt, int lane) {
+    constexpr int W = NRUN * LEN;
+    constexpr int Wp = W <= 1 ? 1 : W <= 2 ? 2 : W <= 4 ? 4 : W <= 8 ? 8 : W <= 16 ? 16 : 32;
+    constexpr int K = 32 / Wp;                       // states per step
+    static_assert(W <= 32, "flush_rows handles at most 32 words per state");
+    const int ds = lane / Wp, c0 = lane - ds * Wp;
+    const bool lane_on = c0 < W;
+    const int c = lane_on ? c0 : 0;                  // idle lanes read word 0 (in bounds) and store nothing
+    const T *src = s_warp + ds * PAD + c;
+    T *dst = g_tile + (long long)ds * OUT + (c < LEN ? off0 + c : off1 + c - LEN);
+    const int left = lane_on ? cnt - ds : 0;         // this lane stores while s0 < left
+#pragma unroll
+    for (int s0 = 0; s0 < 32; s0 += K) st_if_lt(dst + (long long)s0 * OUT, src[s0 * PAD], s0, left);
+}
+
 template <int OUT, int LEN, int PAD, int NRUN>
 __device__ __forceinline__ void flush_runs(float *__restrict__ g_tile, const float *s_warp, int off0, int off1, int cnt,
                                            int lane) {
+    __builtin_assume(__isShared(s_warp));
     constexpr int W = NRUN * LEN;
     constexpr bool EVEN = (LEN % 2 == 0) && (PAD % 2 == 0) && (OUT % 2 == 0);
-    if (EVEN && ((off0 | off1) & 1) == 0 && (reinterpret_cast<unsigned long long>(g_tile) & 7ull) == 0) {
-        constexpr int W2 = W / 2, L2 = LEN / 2;                     // in float2 units
-        constexpr int DS = 32 / W2, DC = 32 % W2;
-        int s = lane / W2, c = lane - s * W2;
-        const float2 *src = reinterpret_cast<const float2 *>(s_warp);
-        float2 *dst = reinterpret_cast<float2 *>(g_tile);
-#pragma unroll 4
-        for (int k = 0; k < W2; k++) {
-            if (s < cnt) dst[(long long)s * (OUT / 2) + (c < L2 ? off0 / 2 + c : off1 / 2 + c - L2)] = src[s * (PAD / 2) + c];
-            s += DS;
-            c += DC;
-            if (c >= W2) { c -= W2; s++; }
+    if constexpr (EVEN && W / 2 <= 32) {
+        if (((off0 | off1) & 1) == 0 && (reinterpret_cast<unsigned long long>(g_tile) & 7ull) == 0) {
+            flush_rows<float2, OUT / 2, LEN / 2, PAD / 2, NRUN>(reinterpret_cast<float2 *>(g_tile),
+                                                               reinterpret_cast<const float2 *>(s_warp), off0 / 2,
+                                                               off1 / 2, cnt, lane);
+            return;
         }
+    }
+    if constexpr (W <= 32) {
+        flush_rows<float, OUT, LEN, PAD, NRUN>(g_tile, s_warp, off0, off1, cnt, lane);
     } else {
         constexpr int DS = 32 / W, DC = 32 % W;
         int s = lane / W, c = lane - s * W;
@@ -75,49 +115,61 @@ struct PipeShape {
     static constexpr int TILE_WORDS = (32 * IN_PAD + 3) / 4 * 4;
     static constexpr int STAGE_WORDS = (32 * P::STAGE_PAD + 3) / 4 * 4;
     // stage 0 stages the input tile and output runs; stage 1 only output runs
-    static constexpr int smem_words(int stage) { return (stage == 0 ? TILE_WORDS : 0) + STAGE_WORDS; }
+    static __host__ __device__ constexpr int smem_words(int stage) { return (stage == 0 ? TILE_WORDS : 0) + STAGE_WORDS; }
 };
 
-// grid = ntasks * ceil(ntiles / WARPS) CTAs; blockIdx.x = task * nblk + blk (tasks sorted by
-// decreasing cost so the long ones start first); warp w of a CTA runs tile blk * WARPS + w.
-// Two instruction-supply facts shape this (tools/micro/ifetch_bench.cu, profiles/r1_micro_ifetch.jsonl):
-// straight-line code beyond the 32 KB SM instruction cache streams at ~0.3 instructions/cycle per
-// warp, and an SM whose warps sit at DIFFERENT places of such a program is capped near 1.0 IPC
-// (each warp pulls its own stream from the GPC cache / L2), whereas warps that run the SAME lines
-// at about the same time share every fetched line (2.7 IPC with 8 warps).  Hence (a) task-major
-// order - all resident warps run one program (tile-major order is 3.2x slower: eight ~100 KB
-// programs thrash the cache, no_instruction stalls 37 per issue); (b) the WARPS warps of a CTA
-// start the same program together and, having no data-dependent control flow, stay in step.
+// Work items are (task, block of WARPS consecutive tiles), numbered task-major (tasks sorted by
+// decreasing cost); warp w of a CTA runs tile blk * WARPS + w.  Instruction supply shapes all of
+// this (tools/micro/ifetch_bench.cu, profiles/r1_micro_ifetch.jsonl): straight-line code beyond the
+// 32 KB SM instruction cache streams at ~0.3 instructions/cycle per warp; an SM whose warps sit at
+// DIFFERENT places of such a program is capped near 1.0 IPC (each warp pulls its own stream from
+// the GPC cache / L2), whereas warps that run the SAME lines at about the same time share every
+// fetched line (2.7 IPC with 8 warps), and SMs that are in step share lines in the GPC cache
+// (2.7 vs 1.6-2.1 IPC).  Hence task-major order (tile-major is 3.2x slower: eight ~100 KB programs
+// thrash the caches), CTAs of WARPS warps that start a program together and re-align at a
+// __syncthreads() every P::SYNC_EVERY operations, and persistent CTAs with a uniform stride.
 template <class P, int STAGE>
 __global__ void __launch_bounds__(32 * P::WARPS, STAGE == 0 ? P::MINB0 : P::MINB1)
 pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0, const float *__restrict__ d_in1,
             float *__restrict__ scratch, int num_states, int ntiles, int nblk, float gravity) {
     using S = PipeShape<P>;
+    constexpr int NTASKS = STAGE == 0 ? P::NTASKS0 : P::NTASKS1;
     extern __shared__ float smem_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int task = blockIdx.x / nblk, blk = blockIdx.x - task * nblk;
-    const int tile = blk * P::WARPS + warp;
-    if (tile >= ntiles) return;                      // no CTA-wide barriers anywhere below
     float *smem = smem_all + warp * S::smem_words(STAGE);
-    const long long first = (long long)tile * 32;
-    const int cnt = min(32, num_states - (int)first);
     float *s_warp = smem + (STAGE == 0 ? S::TILE_WORDS : 0);
-    if (STAGE == 0) {
-        const float *src0 = d_in0 + first * (long long)stride0;
-        if (S::IN_LINEAR && stride0 == P::IN0 && aligned16(src0)) {
-            warp_copy_g2s(smem, src0, cnt * P::IN0, lane);
-        } else {
-            tile_load<P::IN0, S::IN_PAD>(smem, 0, d_in0, first, stride0, cnt, lane);
-            tile_load<P::IN1, S::IN_PAD>(smem, P::IN0, d_in1, first, P::IN1, cnt, lane);
+    // PERSISTENT CTAs walk the (task, block of WARPS tiles) items in task-major order, all with the
+    // same stride: every SM runs the same program at the same time and with the same timing, so
+    // the SMs of a GPC share the instruction stream in the GPC-level cache as well (dynamically
+    // dispatched CTAs drift apart: the identical iiwa14 program runs 1.5-1.7x slower that way).
+    for (int item = blockIdx.x; item < NTASKS * nblk; item += gridDim.x) {
+        const int task = item / nblk, blk = item - task * nblk;
+        // The task programs contain CTA-wide barriers (they keep the warps of the CTA on the same
+        // lines of the program), so a warp past the last tile cannot sit out: it recomputes the
+        // last tile and stores nothing (its scratch writes duplicate the owner's values).
+        const int my_tile = blk * P::WARPS + warp;
+        const bool owner = my_tile < ntiles;
+        const int tile = owner ? my_tile : ntiles - 1;
+        const long long first = (long long)tile * 32;
+        const int cnt = min(32, num_states - (int)first);
+        if (STAGE == 0) {
+            const float *src0 = d_in0 + first * (long long)stride0;
+            if (S::IN_LINEAR && stride0 == P::IN0 && aligned16(src0)) {
+                warp_copy_g2s(smem, src0, cnt * P::IN0, lane);
+            } else {
+                tile_load<P::IN0, S::IN_PAD>(smem, 0, d_in0, first, stride0, cnt, lane);
+                tile_load<P::IN1, S::IN_PAD>(smem, P::IN0, d_in1, first, P::IN1, cnt, lane);
+            }
+            __syncwarp();
         }
+        // lanes past the end of a ragged tile recompute the last valid state; their scratch lane is
+        // private (scratch is allocated in whole tiles) and the flushes only write cnt states
+        const int src = min(lane, cnt - 1);
+        float *sc = scratch + (long long)tile * (P::SCRATCH_WORDS * 32) + lane;
+        P::template run<STAGE>(task, smem + src * S::IN_PAD, sc, sc, s_warp + lane * P::STAGE_PAD,
+                               d_out + first * P::OUT, owner ? cnt : 0, lane, s_warp, gravity);
         __syncwarp();
     }
-    // lanes past the end of a ragged tile recompute the last valid state; their scratch lane is
-    // private (scratch is allocated in whole tiles) and the flushes only write cnt states
-    const int src = min(lane, cnt - 1);
-    float *sc = scratch + (long long)tile * (P::SCRATCH_WORDS * 32) + lane;
-    P::template run<STAGE>(task, smem + src * S::IN_PAD, sc, sc, s_warp + lane * P::STAGE_PAD,
-                           d_out + first * P::OUT, cnt, lane, s_warp, gravity);
 }
 
 template <class P, int STAGE>
@@ -128,23 +180,188 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
     if (ntasks == 0) return cudaSuccess;
     auto kern = pipe_kernel<P, STAGE>;
     constexpr size_t smem_bytes = sizeof(float) * S::smem_words(STAGE) * P::WARPS;
-    static bool configured = false;             // benign race: idempotent attribute set
-    if (!configured) {
+    static int cap = 0;                          // resident CTAs on this device (benign race: idempotent)
+    if (cap == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * P::WARPS, smem_bytes);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        cap = sms * per_sm;
     }
     const int ntiles = (num_states + 31) / 32;
     const int nblk = (ntiles + P::WARPS - 1) / P::WARPS;
-    kern<<<(unsigned)(ntasks * (long long)nblk), 32 * P::WARPS, smem_bytes, stream>>>(
-        d_out, d_in0, stride0, d_in1, scratch, num_states, ntiles, nblk, gravity);
+    const long long items = (long long)ntasks * nblk;
+    const int blocks = (int)(items < cap ? items : cap);
+    kern<<<blocks, 32 * P::WARPS, smem_bytes, stream>>>(d_out, d_in0, stride0, d_in1, scratch, num_states, ntiles,
+                                                        nblk, gravity);
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }
 
-// Both stages on `stream`.  The scratch array comes from the stream-ordered allocator (no
-// library state, safe with concurrent callers on different streams); its pool keeps the memory
-// between calls, so the allocation is a free-list hit after the first launch.
+// ---- fused kernel (experimental, GRID_PIPE_MODE=fused): every SM runs ONE task for the whole launch --
+// The staged kernels walk the tasks one after the other, so an SM changes program every 1-2 items
+// and the stage-1 kernel re-reads the scratch array from HBM once per task.  Here the CTAs (one per
+// SM) are PARTITIONED among the tasks of both stages in proportion to the tasks' instruction counts:
+// CTA `rank` of the m CTAs of a task runs tiles rank, rank + m, ... in ascending order.  Each SM
+// then executes one <= ~100 KB program over and over (its first 64 KB stay in the instruction
+// cache, profiles/r1_ifetch_regions.md), all task groups advance through the tiles at the same
+// rate, so a tile's scratch lines are consumed from L2 right after stage 0 produced them and the
+// output columns of a tile complete their sectors in L2.  Stage-1 warps wait for the stage-0 task
+// of their component on a per-(task, tile) flag (release/acquire at gpu scope).  Dependencies only
+// point to lower CTA indices, which the hardware schedules first, so the kernel cannot deadlock
+// even when not all CTAs are resident at once.
+// The scratch array comes from the stream-ordered allocator (no library state, safe with concurrent
+// callers on different streams); keeping the pool's memory between calls makes the allocation a
+// free-list hit after the first launch.
+static void keep_pool_memory() {
+    static bool done = false;
+    if (done) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done = true;
+}
+
+struct PipePart {
+    short first[64], count[64];
+};
+
+template <class P>
+__global__ void __launch_bounds__(32 * P::WARPS, 1)
+pipe_fused_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0,
+                  const float *__restrict__ d_in1, float *__restrict__ scratch, int *__restrict__ flags, int num_states,
+                  int ntiles, int nblk, float gravity, const PipePart part) {
+    using S = PipeShape<P>;
+    extern __shared__ float smem_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *smem = smem_all + warp * S::smem_words(0);
+    float *s_warp = smem + S::TILE_WORDS;
+    int k = 0;
+    while (k < P::NT - 1 && (int)blockIdx.x >= part.first[k] + part.count[k]) k++;
+    const int rank = blockIdx.x - part.first[k], m = part.count[k];
+    const bool stage0 = k < P::NTASKS0;
+    const int dep = P::dep(k);
+    for (int blk = rank; blk < nblk; blk += m) {
+        const int my_tile = blk * P::WARPS + warp;
+        const bool owner = my_tile < ntiles;
+        const int tile = owner ? my_tile : ntiles - 1;
+        const long long first = (long long)tile * 32;
+        const int cnt = min(32, num_states - (int)first);
+        if (stage0) {
+            const float *src0 = d_in0 + first * (long long)stride0;
+            if (S::IN_LINEAR && stride0 == P::IN0 && aligned16(src0)) {
+                warp_copy_g2s(smem, src0, cnt * P::IN0, lane);
+            } else {
+                tile_load<P::IN0, S::IN_PAD>(smem, 0, d_in0, first, stride0, cnt, lane);
+                tile_load<P::IN1, S::IN_PAD>(smem, P::IN0, d_in1, first, P::IN1, cnt, lane);
+            }
+        } else if (dep >= 0) {
+            if (lane == 0) {
+                const int *f = flags + (long long)dep * ntiles + tile;
+                while (ld_acquire(f) == 0) __nanosleep(200);
+            }
+        }
+        __syncwarp();
+        const int src = min(lane, cnt - 1);
+        float *sc = scratch + (long long)tile * (P::SCRATCH_WORDS * 32) + lane;
+        if (stage0)
+            P::template run<0>(k, smem + src * S::IN_PAD, sc, sc, s_warp + lane * P::STAGE_PAD, d_out + first * P::OUT,
+                               owner ? cnt : 0, lane, s_warp, gravity);
+        else
+            P::template run<1>(k - P::NTASKS0, smem, sc, sc, s_warp + lane * P::STAGE_PAD, d_out + first * P::OUT,
+                               owner ? cnt : 0, lane, s_warp, gravity);
+        if (stage0 && P::SCRATCH_WORDS > 0) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0 && owner) st_release(flags + (long long)k * ntiles + tile, 1);
+        }
+        __syncwarp();
+    }
+}
+
+// CTAs per task: start with one each, then hand the remaining CTAs one at a time to the task with
+// the largest remaining time ceil(nblk / m) * cost (never more CTAs than items).
+template <class P>
+static int pipe_partition(int G, int nblk, PipePart &part) {
+    int m[64];
+    for (int k = 0; k < P::NT; k++) m[k] = 1;
+    for (int used = P::NT; used < G; used++) {
+        int best = -1;
+        long long worst = -1;
+        for (int k = 0; k < P::NT; k++) {
+            if (m[k] >= nblk) continue;
+            const long long load = (long long)((nblk + m[k] - 1) / m[k]) * P::cost(k);
+            if (load > worst) { worst = load; best = k; }
+        }
+        if (best < 0) break;
+        m[best]++;
+    }
+    int at = 0;
+    for (int k = 0; k < P::NT; k++) {
+        part.first[k] = (short)at;
+        part.count[k] = (short)m[k];
+        at += m[k];
+    }
+    return at;
+}
+
+template <class P>
+cudaError_t pipe_fused_launch(float *d_out, const float *d_in0, int stride0, const float *d_in1, int num_states,
+                              float gravity, cudaStream_t stream, bool &handled) {
+    using S = PipeShape<P>;
+    handled = false;
+    auto kern = pipe_fused_kernel<P>;
+    constexpr size_t smem_bytes = sizeof(float) * S::smem_words(0) * P::WARPS;
+    static int cap = 0;
+    if (cap == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * P::WARPS, smem_bytes);
+        if (e != cudaSuccess) return e;
+        cap = per_sm < 1 ? -1 : sms;             // one CTA per SM: an SM never mixes programs
+    }
+    if (cap < P::NT || P::NT > 64) return cudaSuccess;           // not handled: the staged kernels take over
+    const int ntiles = (num_states + 31) / 32;
+    const int nblk = (ntiles + P::WARPS - 1) / P::WARPS;
+    PipePart part;
+    const int blocks = pipe_partition<P>(cap, nblk, part);
+    const size_t sc_bytes = (size_t)ntiles * P::SCRATCH_WORDS * 32 * sizeof(float);
+    const size_t fl_bytes = P::SCRATCH_WORDS > 0 ? (size_t)ntiles * P::NTASKS0 * sizeof(int) : 0;
+    char *buf = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (sc_bytes + fl_bytes > 0) {
+        keep_pool_memory();
+        e = cudaMallocAsync((void **)&buf, sc_bytes + fl_bytes, stream);
+        if (e != cudaSuccess) return e;
+        if (fl_bytes) e = cudaMemsetAsync(buf + sc_bytes, 0, fl_bytes, stream);
+    }
+    if (e == cudaSuccess) {
+        kern<<<blocks, 32 * P::WARPS, smem_bytes, stream>>>(d_out, d_in0, stride0, d_in1, (float *)buf,
+                                                            (int *)(buf + sc_bytes), num_states, ntiles, nblk, gravity,
+                                                            part);
+        g_kernel_launches.fetch_add(1);
+        e = cudaGetLastError();
+    }
+    if (buf) {
+        cudaError_t e2 = cudaFreeAsync(buf, stream);
+        if (e == cudaSuccess) e = e2;
+    }
+    handled = true;
+    return e;
+}
+
+// Entry point: both stages on `stream` (or the experimental fused kernel, see below).
 template <class P>
 cudaError_t pipe_launch(float *d_out, const float *d_in0, int stride0, const float *d_in1, int num_states,
                         float gravity, cudaStream_t stream) {
@@ -152,18 +369,19 @@ cudaError_t pipe_launch(float *d_out, const float *d_in0, int stride0, const flo
     g_calls.fetch_add(1);
     float *scratch = nullptr;
     cudaError_t e;
+    // GRID_PIPE_MODE=fused selects the SM-partitioned single-kernel variant.  It is correct (tests run
+    // it) but measured SLOWER than the staged kernels on every robot (Atlas FD gradient 975 vs 760 us,
+    // HyQ 56 vs 43 us, profiles/r1_pipe_fused_vs_staged.md): SMs of one GPC running different programs
+    // lose the sharing of the instruction stream in the GPC-level cache.
+    const char *f = getenv("GRID_PIPE_MODE");
+    const bool fused = f && !strcmp(f, "fused");
+    if (fused && P::NT > 1) {
+        bool handled = false;
+        e = pipe_fused_launch<P>(d_out, d_in0, stride0, d_in1, num_states, gravity, stream, handled);
+        if (handled || e != cudaSuccess) return e;
+    }
     if (P::SCRATCH_WORDS > 0) {
-        static bool pool_ready = false;
-        if (!pool_ready) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                unsigned long long keep = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            pool_ready = true;
-        }
+        keep_pool_memory();
         const size_t ntiles = (size_t)(num_states + 31) / 32;
         e = cudaMallocAsync((void **)&scratch, ntiles * P::SCRATCH_WORDS * 32 * sizeof(float), stream);
         if (e != cudaSuccess) return e;

@@ -68,9 +68,11 @@ def subrobot(robot: Robot, ids: Sequence[int], name: Optional[str] = None) -> Ro
 class PipeTask:
     """One traced program = one thread per (state, task)."""
 
-    def __init__(self, name: str, stage: int, program: Program, runs: List[Tuple[Tuple[int, ...], int]]):
-        self.name, self.stage, self.program, self.runs = name, stage, program, runs
+    def __init__(self, name: str, stage: int, program: Program, runs: List[Tuple[Tuple[int, ...], int]],
+                 comp: int = 0):
+        self.name, self.stage, self.program, self.runs, self.comp = name, stage, program, runs, comp
         self.counts = program.op_counts()
+        self.cost = self.counts["nodes"]              # refined by emit_task (instructions, incl. loads and flushes)
 
     @property
     def flops(self) -> int:
@@ -260,7 +262,7 @@ class PipeVariant:
         sc_base = 0
         for ci, ids in enumerate(components(robot)):
             pf, runs = _trace_full(robot, ids, alg, use_qdd)
-            full = PipeTask("c%d_full" % ci, 0, pf, runs)
+            full = PipeTask("c%d_full" % ci, 0, pf, runs, ci)
             if alg not in ("id_grad", "fd_grad") or full.flops <= single_stage_max_flops:
                 if full.flops > stage_a_max_flops:
                     self.feasible = False
@@ -297,12 +299,12 @@ class PipeVariant:
             sc_base += len(word_of)
             for node, w in word_of.items():
                 pa.output("sc", w, V(pa, i=node))
-            ta = PipeTask("c%d_A" % ci, 0, pa, [])
+            ta = PipeTask("c%d_A" % ci, 0, pa, [], ci)
             if ta.flops > stage_a_max_flops:
                 self.feasible = False
             self.tasks.append(ta)
             for gi, J, pb, runs in btasks:
-                t = PipeTask("c%d_B%d_j%d_%d" % (ci, gi, ids[J[0]], ids[J[-1]]), 1, pb, runs)
+                t = PipeTask("c%d_B%d_j%d_%d" % (ci, gi, ids[J[0]], ids[J[-1]]), 1, pb, runs, ci)
                 if t.flops > stage_a_max_flops:          # a single column too long for one thread (64-link chain)
                     self.feasible = False
                 t.sc_word = {("sc:%d" % node): w for node, w in word_of.items()}
@@ -339,7 +341,7 @@ class PipeVariant:
 
     def summary(self) -> Dict[str, object]:
         return {"flops": self.flops, "scratch_words": self.scratch_words,
-                "tasks": [(t.name, t.stage, t.flops) for st in self.stage_tasks for t in st]}
+                "tasks": [(t.name, t.stage, t.flops, getattr(t, "instr", 0)) for st in self.stage_tasks for t in st]}
 
 
 # ---- emission ----------------------------------------------------------------------------------
@@ -351,7 +353,7 @@ def _flit(x: float) -> str:
 
 
 def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead: int = 24,
-              scratch_lead: int = 160, indent: str = "        ") -> List[str]:
+              scratch_lead: int = 160, indent: str = "        ", sync_every: int = 0) -> List[str]:
     """One task as a __device__ function.  Input loads are issued `lead` operations before
     their first use (long enough to cover the L2 latency of scratch reads, short enough not to
     pin registers); output runs are flushed as soon as their last value exists."""
@@ -378,7 +380,7 @@ def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead
         elif name.startswith("in:"):
             stmt, lead = "const float t%d = s_in[%d];" % (o, int(name[3:])), tile_lead
         else:
-            stmt, lead = "const float t%d = __ldg(sc_in + %d);" % (o, 32 * sc_word[name]), scratch_lead
+            stmt, lead = "const float t%d = pipe::ldsc(sc_in + %d);" % (o, 32 * sc_word[name]), scratch_lead
         load_pos[o] = max(0, fu - lead)
         loads_at.setdefault(load_pos[o], []).append(indent + stmt)
 
@@ -429,12 +431,18 @@ def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead
     body: List[str] = ["    // %s: %d mul + %d add per state" % (t.name, t.counts["mul"], t.counts["add"]),
                        "    static __device__ __noinline__ void %s(const float *s_in, const float *__restrict__ sc_in,"
                        " float *__restrict__ sc_out, float *s_stage, float *__restrict__ g_tile, const int cnt,"
-                       " const int lane, const float *s_warp, const float gravity) {" % fname]
+                       " const int lane, const float *s_warp, const float gravity) {" % fname,
+                       # the call boundary hides the address space: without this the staging accesses
+                       # compile to generic LD/ST instead of LDS/STS
+                       indent + "__builtin_assume(__isShared(s_in)); __builtin_assume(__isShared(s_stage));"
+                                " __builtin_assume(__isShared(s_warp));"]
     body += sc_at.get(-1, [])
     for ri in flush_at.get(-1, []):
         body += flush(ri)
     sincos_done = set()
     for c in range(max(1, len(order))):
+        if sync_every and c and c % sync_every == 0:
+            body.append(indent + "__syncthreads();")
         body += loads_at.get(c, [])
         i = order[c] if c < len(order) else None
         k = p.nodes[i] if i is not None else ("nop",)
@@ -465,10 +473,19 @@ def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead
         for ri in flush_at.get(c, []):
             body += flush(ri)
     body.append("    }")
+    # instruction estimate for the SM partition of the fused kernel: operations, loads, scratch stores,
+    # staging stores and the unrolled flush rows; code beyond the 64 KB the instruction cache keeps
+    # runs ~3.4x slower per instruction (profiles/r1_ifetch_regions.md)
+    n_instr = len(order) + len(first_use) + sum(len(v) for v in sc_at.values())
+    n_instr += sum(len(offs) * ln + 48 for (offs, ln) in t.runs)
+    n_sass = int(0.8 * n_instr)                  # mul+add pairs fuse into FFMA
+    t.cost = int(min(n_sass, 4096) + 3.4 * max(0, n_sass - 4096))
+    t.instr = n_instr
     return body
 
 
-def emit_pipe_struct(pv: PipeVariant, min_blocks: Tuple[int, int] = (1, 1), warps: int = 8) -> Tuple[str, Dict[str, object]]:
+def emit_pipe_struct(pv: PipeVariant, min_blocks: Tuple[int, int] = (1, 1), warps: int = 8,
+                     sync_every: int = 256) -> Tuple[str, Dict[str, object]]:
     """min_blocks: resident CTAs per SM the two stage kernels are compiled for (register cap =
     65536 / (32 * warps * min_blocks)); warps: tiles (warps) per CTA."""
     max_run = max([len(offs) * ln for t in pv.tasks for (offs, ln) in t.runs] + [1])
@@ -483,10 +500,11 @@ def emit_pipe_struct(pv: PipeVariant, min_blocks: Tuple[int, int] = (1, 1), warp
                pv.in0, pv.in1, pv.out, pv.scratch_words, stage_pad),
            "    static constexpr int NTASKS0 = %d, NTASKS1 = %d, MINB0 = %d, MINB1 = %d, WARPS = %d;" % (
                len(pv.stage_tasks[0]), len(pv.stage_tasks[1]), min_blocks[0], min_blocks[1], warps),
-           "    static constexpr long long TRACED_FLOPS = %d;" % pv.flops]
+           "    static constexpr long long TRACED_FLOPS = %d;" % pv.flops,
+           "    static constexpr int SYNC_EVERY = %d;" % (sync_every if warps > 1 else 0)]
     for s in (0, 1):
         for ti, t in enumerate(pv.stage_tasks[s]):
-            txt += emit_task(t, "s%d_t%d" % (s, ti), pv.out, stage_pad)
+            txt += emit_task(t, "s%d_t%d" % (s, ti), pv.out, stage_pad, sync_every=sync_every if warps > 1 else 0)
     txt.append("    template <int STAGE> static __device__ __forceinline__ void run(const int task, const float *s_in,"
                " const float *__restrict__ sc_in, float *__restrict__ sc_out, float *s_stage,"
                " float *__restrict__ g_tile, const int cnt, const int lane, const float *s_warp, const float gravity) {")
@@ -501,5 +519,15 @@ def emit_pipe_struct(pv: PipeVariant, min_blocks: Tuple[int, int] = (1, 1), warp
         txt.append("            default: break;")
         txt.append("            }")
         txt.append("        }")
-    txt += ["    }", "};", ""]
+    txt += ["    }"]
+    # fused kernel (grid_pipe.cuh pipe_fused_kernel): tasks of both stages numbered stage 0 first
+    allt = pv.stage_tasks[0] + pv.stage_tasks[1]
+    a_index = {t.comp: i for i, t in enumerate(pv.stage_tasks[0])}
+    txt.append("    static constexpr int NT = %d;" % len(allt))
+    txt.append("    static constexpr int cost(int k) { return %s; }   // estimated instructions per tile" % (
+        " ".join("k == %d ? %d :" % (i, t.cost) for i, t in enumerate(allt)) + " 0"))
+    txt.append("    // stage-0 task whose scratch words task k reads (-1: none)")
+    txt.append("    static __host__ __device__ constexpr int dep(int k) { return %s; }" % (
+        " ".join("k == %d ? %d :" % (i, a_index[t.comp]) for i, t in enumerate(allt) if t.stage == 1) + " -1"))
+    txt += ["};", ""]
     return "\n".join(txt), pv.summary()

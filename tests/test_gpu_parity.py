@@ -242,6 +242,22 @@ def test_pipe_ragged_batches_atlas(N, alg, monkeypatch):
     assert np.array_equal(g[1:N + 1], big[:N])
 
 
+@pytest.mark.parametrize("name,N", [("atlas", 1000), ("hyq", 4099)])
+def test_pipe_fused_variant_matches_staged(name, N, monkeypatch):
+    """The SM-partitioned single-kernel variant (GRID_PIPE_MODE=fused: stage-1 warps wait on
+    release/acquire flags of stage 0) computes exactly what the two staged kernels compute."""
+    monkeypatch.setenv("GRID_FORCE_KERNEL", "pipe")
+    robot = load_named_robot(name)
+    eng = get_engine(robot)
+    q, qd, u, _ = make_states(robot.n, N, 77)
+    for alg in ("fd", "id_grad", "fd_grad"):
+        monkeypatch.delenv("GRID_PIPE_MODE", raising=False)
+        staged = run_alg(eng, alg, q, qd, u)
+        monkeypatch.setenv("GRID_PIPE_MODE", "fused")
+        for _ in range(3):
+            assert np.array_equal(run_alg(eng, alg, q, qd, u), staged), alg
+
+
 @pytest.mark.parametrize("name,family", [("atlas", "wps"), ("atlas", "pipe"), ("iiwa14", "tps"), ("iiwa14", "cps"),
                                          ("mixed5", "wps")])
 def test_repeated_launches_are_bit_identical(name, family, monkeypatch):

@@ -66,7 +66,8 @@ def test_every_output_word_has_exactly_one_writer_and_emission_is_deterministic(
     a, _ = emit_pipe_struct(pv)
     b, _ = emit_pipe_struct(PipeVariant(robot, "fd_grad"))
     assert a == b
-    assert "flush2<" in a and "__ldg(sc_in" in a and "sc_out[" in a
+    assert "flush2<" in a and "pipe::ldsc(sc_in" in a and "sc_out[" in a and "__syncthreads();" in a
+    assert "static constexpr int NT = %d;" % len(pv.tasks) in a
 
 
 def test_plan_policy():

@@ -5,7 +5,7 @@
 // `no_instruction` stalls.  This microbenchmark isolates that: a body of B independent-chain FFMAs
 // (8 accumulators, so dependencies never bind), executed `iters` times, with W warps per SM that
 // either start together or are de-phased by a busy-wait so that they sit at different places of
-// the body.  Output: JSON lines with the achieved instructions/cycle per SM.
+// the body (dephase > 0), or whole SMs are de-phased against each other (dephase < 0).  Output: JSON lines with the achieved instructions/cycle per SM.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ifetch_bench ifetch_bench.cu && ./ifetch_bench
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -32,9 +32,12 @@ __global__ void __launch_bounds__(512) k(float *out, int iters, int dephase, flo
 #pragma unroll
     for (int i = 0; i < 8; i++) x[i] = threadIdx.x * 1e-3f + i;
     const int warp = threadIdx.x >> 5;
-    if (dephase > 0) {
+    if (dephase > 0) {             // de-phase the warps of an SM
         const long long t0 = clock64();
         while (clock64() - t0 < (long long)dephase * warp) { }
+    } else if (dephase < 0) {      // warps of an SM start together, SMs are de-phased against each other
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)(-dephase) * (blockIdx.x % 37)) { }
     }
 #pragma unroll 1
     for (int it = 0; it < iters; it++) Body<B>::run(x, a, b);
@@ -74,7 +77,7 @@ int main() {
     float *d;
     cudaMalloc(&d, 4);
     const int warps[] = {1, 4, 8, 16};
-    const int deph[] = {0, 3000};
+    const int deph[] = {0, 3000, -3000};
     for (int w : warps)
         for (int dp : deph) {
             if (w == 1 && dp) continue;
