@@ -25,12 +25,15 @@ GEN_DIR = os.path.join(PKG, "_generated")
 LIB_DIR = os.path.join(PKG, "_lib")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-gnu-unique", "-shared", "-split-compile=0"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-gnu-unique", "-shared"]
+# (-split-compile=0 halves the build time of the Atlas library but costs ~4 % more instructions in the
+# straight-line kernels - 8 896 vs 8 544 for the iiwa14 FD gradient - so it is not used.)
 
 
 def _static_hash() -> str:
     h = hashlib.sha256()
     h.update(CODEGEN_VERSION.encode())
+    h.update(" ".join(NVCC_FLAGS).encode())
     for d in (CSRC, INCLUDE):
         for fn in sorted(os.listdir(d)):
             if fn.endswith((".cuh", ".h", ".cu")):
