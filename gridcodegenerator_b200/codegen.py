@@ -511,7 +511,7 @@ class KernelPlan:
                  wps_max_states: int = 0, cps_max_states: int = 2048, tps_loop_columns: bool = False,
                  tps_pairs: bool = False, tps_v2_park=None, pipe_algs=None, pipe_min_states: int = 0,
                  pipe_opts: Optional[Dict[str, int]] = None, pipe_min_blocks: Tuple[int, int] = (1, 1),
-                 pipe_warps: int = 8, pipe_sync_every: int = 256):
+                 pipe_warps: int = 8, pipe_sync_every: int = 256, pipe_scratch_lead: int = 160):
         self.robot = robot
         self.tps_warps = tps_warps
         self.tps_sync_every = tps_sync_every if tps_warps > 1 else 0
@@ -540,6 +540,7 @@ class KernelPlan:
         self.pipe_min_blocks = tuple(pipe_min_blocks)
         self.pipe_warps = pipe_warps
         self.pipe_sync_every = pipe_sync_every
+        self.pipe_scratch_lead = pipe_scratch_lead
         self.pipe: Dict[str, "PipeVariant"] = {}
         if pipe_algs is None:
             # a forest of several trees: one thread per (state, tree) beats one thread per state
@@ -639,7 +640,8 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
     if plan.pipe:
         from .pipeline import emit_pipe_struct
         for v, pv in plan.pipe.items():
-            txt, summ = emit_pipe_struct(pv, plan.pipe_min_blocks, plan.pipe_warps, plan.pipe_sync_every)
+            txt, summ = emit_pipe_struct(pv, plan.pipe_min_blocks, plan.pipe_warps, plan.pipe_sync_every,
+                                         plan.pipe_scratch_lead)
             out.append(txt)
             stats["pipe_" + v] = summ
     out.append("}}  // namespace GRID_NS::gen\n")

@@ -485,7 +485,7 @@ def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead
 
 
 def emit_pipe_struct(pv: PipeVariant, min_blocks: Tuple[int, int] = (1, 1), warps: int = 8,
-                     sync_every: int = 256) -> Tuple[str, Dict[str, object]]:
+                     sync_every: int = 256, scratch_lead: int = 160) -> Tuple[str, Dict[str, object]]:
     """min_blocks: resident CTAs per SM the two stage kernels are compiled for (register cap =
     65536 / (32 * warps * min_blocks)); warps: tiles (warps) per CTA."""
     max_run = max([len(offs) * ln for t in pv.tasks for (offs, ln) in t.runs] + [1])
@@ -504,7 +504,8 @@ def emit_pipe_struct(pv: PipeVariant, min_blocks: Tuple[int, int] = (1, 1), warp
            "    static constexpr int SYNC_EVERY = %d;" % (sync_every if warps > 1 else 0)]
     for s in (0, 1):
         for ti, t in enumerate(pv.stage_tasks[s]):
-            txt += emit_task(t, "s%d_t%d" % (s, ti), pv.out, stage_pad, sync_every=sync_every if warps > 1 else 0)
+            txt += emit_task(t, "s%d_t%d" % (s, ti), pv.out, stage_pad, sync_every=sync_every if warps > 1 else 0,
+                             scratch_lead=scratch_lead)
     txt.append("    template <int STAGE> static __device__ __forceinline__ void run(const int task, const float *s_in,"
                " const float *__restrict__ sc_in, float *__restrict__ sc_out, float *s_stage,"
                " float *__restrict__ g_tile, const int cnt, const int lane, const float *s_warp, const float gravity) {")

@@ -199,6 +199,43 @@ def test_host_path_grid_data():
     data.close()
 
 
+def test_host_path_grid_data_atlas_phase_split():
+    """gridData flow on Atlas: the host path pipelines chunks over several streams, each chunk a
+    phase-split launch with its own stream-ordered scratch array."""
+    robot = load_named_robot("atlas")
+    eng = get_engine(robot)
+    n, N = robot.n, 9000
+    q, qd, u, _ = make_states(n, N, 18)
+    data = eng.make_data(N)
+    data.h["q_qd_u"][:] = pack_q_qd_u(q, qd, u)
+    for _ in range(2):
+        assert np.array_equal(data.forward_dynamics_gradient(N).copy(), run_alg(eng, "fd_grad", q, qd, u))
+    assert np.array_equal(data.forward_dynamics(N).copy(), run_alg(eng, "fd", q, qd, u))
+    assert np.array_equal(data.direct_minv(N).copy(), run_alg(eng, "minv", q, qd, u))
+    assert np.array_equal(data.inverse_dynamics_gradient(N).copy(), run_alg(eng, "id_grad", q, qd, u))
+    data.close()
+
+
+def test_phase_split_concurrent_streams():
+    """Two streams, two batches, launches interleaved: results equal the serial ones (the scratch
+    arrays are per call)."""
+    robot = load_named_robot("atlas")
+    eng = get_engine(robot)
+    n = robot.n
+    qa, qda, ua, _ = make_states(n, 3000, 31)
+    qb, qdb, ub, _ = make_states(n, 2500, 32)
+    ra, rb = run_alg(eng, "fd_grad", qa, qda, ua), run_alg(eng, "fd_grad", qb, qdb, ub)
+    xa, xb = dev(pack_q_qd_u(qa, qda, ua)), dev(pack_q_qd_u(qb, qdb, ub))
+    oa, ob = torch.empty(3000, 2 * n * n, device="cuda"), torch.empty(2500, 2 * n * n, device="cuda")
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(4):
+        eng.forward_dynamics_gradient_device(oa, xa, stream=sa)
+        eng.forward_dynamics_gradient_device(ob, xb, stream=sb)
+    torch.cuda.synchronize()
+    assert np.array_equal(oa.cpu().numpy(), ra) and np.array_equal(ob.cpu().numpy(), rb)
+
+
 @pytest.mark.parametrize("name,N,algs", [("iiwa14", 65536, ALL), ("hyq", 16384, ALL), ("atlas", 4096, ALL),
                                          ("chain64", 256, ALL), ("mixed5", 8192, ALL)])
 def test_full_batches_against_c_oracle(name, N, algs):
