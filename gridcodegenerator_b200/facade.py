@@ -569,7 +569,16 @@ class GRiDCodeGenerator:
         text = open(os.path.join(_PKG, "csrc", "grid_tps.cuh")).read().replace("#pragma once", "")
         self.gen_add_code_line("#define GRID_NS %s" % self._impl_ns)
         self.code_str += text
+        if self._plan.pipe:     # phase-split kernels: the host functions of the large robots launch them
+            self.code_str += open(os.path.join(_PKG, "csrc", "grid_pipe.cuh")).read().replace(
+                "#pragma once", "").replace('#include "grid_tps.cuh"', "")
         self.gen_add_code_line("namespace GRID_NS { namespace gen {")
+        if self._plan.pipe:
+            from .pipeline import emit_pipe_struct
+            for v, pv in self._plan.pipe.items():
+                txt, _ = emit_pipe_struct(pv, self._plan.pipe_min_blocks, self._plan.pipe_warps,
+                                          self._plan.pipe_sync_every, self._plan.pipe_scratch_lead)
+                self.code_str += txt
         for alg, variants in (("id", ("id", "id_qdd")), ("minv", ("minv",)), ("fd", ("fd",)),
                               ("id_grad", ("id_grad", "id_grad_qdd")), ("fd_grad", ("fd_grad", "fd_grad_qdd_minv"))):
             if self._family[alg] != "tps":
@@ -737,6 +746,8 @@ class GRiDCodeGenerator:
             lines += ["    " + c for c in copies_in] + ["    gpuErrchk(cudaDeviceSynchronize());"]
         if single:
             lines.append("    struct timespec start, end; clock_gettime(CLOCK_MONOTONIC,&start);")
+        if not single and "pipe" in self._plan.kind.get(alg_key, ""):
+            kernel_calls = [self._pipe_host_call(k, alg_key) for k in kernel_calls]
         lines += ["    " + k.replace("KERNEL<T>", ("%s_kernel%s<T>" % (fn, "_single_timing" if single else "")))
                   .replace("<<<>>>", "<<<blocks_,SUGGESTED_THREADS,smem_>>>")
                   .replace("NT_", "num_timesteps") for k in kernel_calls]
@@ -750,6 +761,25 @@ class GRiDCodeGenerator:
             lines.append("    printf(\"Single Call %s %%fus\\n\",time_delta_us_timespec(start,end)/"
                          "static_cast<double>(num_timesteps));" % code)
         self.gen_add_code_lines(lines + ["}", ""])
+
+    def _pipe_host_call(self, line: str, alg_key: str) -> str:
+        """Rewrites `KERNEL<T><<<>>>(out, in, stride, [d_qdd,] d_robotModel, [gravity,] NT_)` into a launch of
+        the phase-split kernels (csrc/grid_pipe.cuh) on the default stream, where a variant exists; the
+        reference-signature `_kernel` (wide kernel) stays available for callers that launch it themselves."""
+        import re
+        names = {"minv": ("PipeMinv", None), "fd": ("PipeFd", None), "id": ("PipeId", "PipeIdQdd"),
+                 "id_grad": ("PipeIdGrad", "PipeIdGradQdd"), "fd_grad": ("PipeFdGrad", None)}[alg_key]
+
+        def sub(m):
+            args = [a.strip() for a in m.group(1).split(",")]
+            extras = args[3:args.index("d_robotModel")]
+            if len(extras) > 1 or (extras and names[1] is None):
+                return m.group(0)                      # no phase-split variant (USE_QDD_MINV_FLAG): wide kernel
+            struct = names[1] if extras else names[0]
+            g = "gravity" if "gravity" in args else "0.f"
+            return "gpuErrchk(%s::pipe::pipe_launch<%s::gen::%s>(%s, %s, %s, %s, num_timesteps, %s, 0));" % (
+                self._impl_ns, self._impl_ns, struct, args[0], args[1], args[2], extras[0] if extras else "nullptr", g)
+        return re.sub(r"KERNEL<T><<<>>>\(([^;]*)\);", sub, line)
 
     _H2D = "gpuErrchk(cudaMemcpyAsync(hd_data->d_%s,hd_data->h_%s,%s*T_*sizeof(T),cudaMemcpyHostToDevice,streams[%d]));"
 

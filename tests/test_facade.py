@@ -125,8 +125,9 @@ def test_emitted_header_compiles_for_sm100a(name):
 @pytest.mark.parametrize("name,N", [("iiwa14", 200), ("atlas", 40)])
 def test_emitted_header_host_and_device_functions_on_gpu(tmp_path, name, N):
     """iiwa14: every kernel is a thread-per-state program and the _inner/_device functions exist.
-    atlas: inverse dynamics is thread-per-state, the other four kernels are the wide CTA-per-state
-    kernels behind the same reference signatures (no _inner/_device functions)."""
+    atlas: inverse dynamics is thread-per-state; the host functions of the other four algorithms launch the
+    phase-split kernels (the USE_QDD_MINV_FLAG overload and the reference-signature _kernel entry points are
+    the wide CTA-per-state kernels); no _inner/_device functions."""
     from gridcodegenerator_b200.header_build import build_header_harness
     robot = load_named_robot(name)
     n = robot.n
