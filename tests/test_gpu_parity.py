@@ -279,6 +279,31 @@ def test_pipe_ragged_batches_atlas(N, alg, monkeypatch):
     assert np.array_equal(g[1:N + 1], big[:N])
 
 
+@pytest.mark.parametrize("name", ["iiwa14", "mixed5"])
+@pytest.mark.parametrize("mode", ["staged", "fused"])
+def test_forced_split_of_single_tree_robots(name, mode, monkeypatch):
+    """A serial chain (iiwa14) and a tree with prismatic joints (mixed5) forced through the
+    state-program + one-column-program-per-joint split (library variant built by
+    __graft_entry__.build()): same answers as the oracle, ragged batch, both launch modes."""
+    import __graft_entry__ as G
+    from gridcodegenerator_b200.runtime import GridEngine
+    robot = load_named_robot(name)
+    eng = GridEngine(robot, plan=G.split_test_plan(robot), tag=G.SPLIT_TEST_TAG)
+    monkeypatch.setenv("GRID_FORCE_KERNEL", "pipe")
+    if mode == "fused":
+        monkeypatch.setenv("GRID_PIPE_MODE", "fused")
+    N = 1000
+    q, qd, u, qdd = make_states(robot.n, N, seed_for(name) + 3)
+    q64, qd64, u64, qdd64 = (x.astype(np.float64) for x in (q, qd, u, qdd))
+    for alg, kw, ref in (("id_grad", {}, O.batch(robot, "id_grad", q64[:128], qd64[:128])),
+                         ("id_grad", dict(qdd=qdd), O.batch(robot, "id_grad", q64[:128], qd64[:128], qdd64[:128])),
+                         ("fd_grad", {}, O.batch(robot, "fd_grad", q64[:128], qd64[:128], u64[:128]))):
+        assert "pipe" in eng.kernel_kind(alg)
+        out = run_alg(eng, alg, q, qd, u, **kw)
+        assert relerr(out[:128], ref) < TOL[alg], (name, alg, relerr(out[:128], ref))
+        assert np.isfinite(out).all()
+
+
 @pytest.mark.parametrize("name,N", [("atlas", 1000), ("hyq", 4099)])
 def test_pipe_fused_variant_matches_staged(name, N, monkeypatch):
     """The SM-partitioned single-kernel variant (GRID_PIPE_MODE=fused: stage-1 warps wait on

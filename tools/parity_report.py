@@ -29,7 +29,7 @@ for name, N in SIZES.items():
                              ("id_grad", 2 * n * n, eng.inverse_dynamics_gradient_device),
                              ("fd_grad", 2 * n * n, eng.forward_dynamics_gradient_device)):
         ref = C.batch(robot, alg, q64, qd64, u64 if alg in ("fd", "fd_grad") else None)
-        for fam in ("tps", "wps", "cps"):
+        for fam in ("tps", "wps", "cps", "pipe"):
             if fam not in eng.kernel_kind(alg):
                 continue
             os.environ["GRID_FORCE_KERNEL"] = fam
