@@ -131,10 +131,12 @@ struct PipeShape {
 template <class P, int STAGE>
 __global__ void __launch_bounds__(32 * P::WARPS, STAGE == 0 ? P::MINB0 : P::MINB1)
 pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0, const float *__restrict__ d_in1,
-            float *__restrict__ scratch, int num_states, int ntiles, int nblk, float gravity) {
+            float *__restrict__ scratch, unsigned int *__restrict__ ticket, int num_states, int ntiles, int nblk,
+            float gravity) {
     using S = PipeShape<P>;
     constexpr int NTASKS = STAGE == 0 ? P::NTASKS0 : P::NTASKS1;
     extern __shared__ float smem_all[];
+    __shared__ int s_item;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *smem = smem_all + warp * S::smem_words(STAGE);
     float *s_warp = smem + (STAGE == 0 ? S::TILE_WORDS : 0);
@@ -142,7 +144,20 @@ pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stri
     // same stride: every SM runs the same program at the same time and with the same timing, so
     // the SMs of a GPC share the instruction stream in the GPC-level cache as well (dynamically
     // dispatched CTAs drift apart: the identical iiwa14 program runs 1.5-1.7x slower that way).
-    for (int item = blockIdx.x; item < NTASKS * nblk; item += gridDim.x) {
+    // Items are handed out in task-major order: with a ticket counter when there are more items than
+    // CTAs (tasks differ in length - Atlas stage 0: 27 k vs 12 k cost units - and a fixed stride leaves
+    // some CTAs with two long items and others with one), with a fixed stride otherwise.
+    for (int iter = 0;; iter++) {
+        int item;
+        if (ticket) {
+            if (threadIdx.x == 0) s_item = (int)atomicAdd(ticket, 1u);
+            __syncthreads();
+            item = s_item;
+            __syncthreads();
+        } else {
+            item = blockIdx.x + iter * gridDim.x;
+        }
+        if (item >= NTASKS * nblk) break;
         const int task = item / nblk, blk = item - task * nblk;
         // The task programs contain CTA-wide barriers (they keep the warps of the CTA on the same
         // lines of the program), so a warp past the last tile cannot sit out: it recomputes the
@@ -174,7 +189,7 @@ pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stri
 
 template <class P, int STAGE>
 cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, const float *d_in1, float *scratch,
-                              int num_states, float gravity, cudaStream_t stream) {
+                              unsigned int *ticket, int num_states, float gravity, cudaStream_t stream) {
     using S = PipeShape<P>;
     constexpr int ntasks = STAGE == 0 ? P::NTASKS0 : P::NTASKS1;
     if (ntasks == 0) return cudaSuccess;
@@ -196,8 +211,8 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
     const int nblk = (ntiles + P::WARPS - 1) / P::WARPS;
     const long long items = (long long)ntasks * nblk;
     const int blocks = (int)(items < cap ? items : cap);
-    kern<<<blocks, 32 * P::WARPS, smem_bytes, stream>>>(d_out, d_in0, stride0, d_in1, scratch, num_states, ntiles,
-                                                        nblk, gravity);
+    kern<<<blocks, 32 * P::WARPS, smem_bytes, stream>>>(d_out, d_in0, stride0, d_in1, scratch,
+                                                        ticket, num_states, ntiles, nblk, gravity);
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -380,14 +395,57 @@ cudaError_t pipe_launch(float *d_out, const float *d_in0, int stride0, const flo
         e = pipe_fused_launch<P>(d_out, d_in0, stride0, d_in1, num_states, gravity, stream, handled);
         if (handled || e != cudaSuccess) return e;
     }
-    if (P::SCRATCH_WORDS > 0) {
-        keep_pool_memory();
-        const size_t ntiles = (size_t)(num_states + 31) / 32;
-        e = cudaMallocAsync((void **)&scratch, ntiles * P::SCRATCH_WORDS * 32 * sizeof(float), stream);
-        if (e != cudaSuccess) return e;
+    // Two-stage variants can run in chunks of P::CHUNK_STATES states (a multiple of 32; GRID_PIPE_CHUNK
+    // overrides; 0 = one chunk, the default): the scratch words of a chunk would then still be in L2
+    // when stage 1 reads them.  Measured (profiles/r1_pipe_order.md): chunking LOSES (Atlas FD gradient
+    // 769 us unchunked, 789 / 979 / 1083 us with 32 k / 16 k / 8 k chunks) - fewer tiles per task per SM
+    // means less re-execution of a program while it is in the instruction caches.
+    int chunk = num_states;
+    static int chunk_cfg = -1;
+    if (chunk_cfg < 0) {
+        const char *c = getenv("GRID_PIPE_CHUNK");
+        chunk_cfg = c ? atoi(c) / 32 * 32 : P::CHUNK_STATES;
     }
-    e = pipe_stage_launch<P, 0>(d_out, d_in0, stride0, d_in1, scratch, num_states, gravity, stream);
-    if (e == cudaSuccess) e = pipe_stage_launch<P, 1>(d_out, d_in0, stride0, d_in1, scratch, num_states, gravity, stream);
+    if (P::SCRATCH_WORDS > 0 && chunk_cfg > 0 && chunk_cfg < num_states) chunk = chunk_cfg;
+    const int nchunks = (num_states + chunk - 1) / chunk;
+    // one allocation: [ticket counters: 2 per chunk, padded to 256 B | scratch words of one chunk];
+    // small batches need no tickets, single-stage variants no scratch
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    constexpr int max_tasks = P::NTASKS0 > P::NTASKS1 ? P::NTASKS0 : P::NTASKS1;
+    const long long max_items = (long long)max_tasks * (((chunk + 31) / 32 + P::WARPS - 1) / P::WARPS);
+    // (the counters cost a memset node: ~1.5 us, visible on 10 us launches such as HyQ Minv at 16 384
+    // states - only worth it when every CTA takes several items)
+    const bool use_tickets = max_items > 4LL * sms;
+    const size_t tk_bytes = use_tickets ? ((size_t)nchunks * 2 * sizeof(unsigned int) + 255) / 256 * 256 : 0;
+    const size_t sc_bytes = (size_t)((chunk + 31) / 32) * P::SCRATCH_WORDS * 32 * sizeof(float);
+    unsigned int *tickets = nullptr;
+    float *sc = nullptr;
+    e = cudaSuccess;
+    if (tk_bytes + sc_bytes > 0) {
+        keep_pool_memory();
+        e = cudaMallocAsync((void **)&scratch, tk_bytes + sc_bytes, stream);
+        if (e != cudaSuccess) return e;
+        sc = reinterpret_cast<float *>(reinterpret_cast<char *>(scratch) + tk_bytes);
+        if (use_tickets) {
+            tickets = reinterpret_cast<unsigned int *>(scratch);
+            e = cudaMemsetAsync(tickets, 0, tk_bytes, stream);
+        }
+    }
+    for (int c = 0; c < nchunks && e == cudaSuccess; c++) {
+        const int first = c * chunk;
+        const int n = num_states - first < chunk ? num_states - first : chunk;
+        float *o = d_out + (long long)first * P::OUT;
+        const float *i0 = d_in0 + (long long)first * stride0;
+        const float *i1 = d_in1 ? d_in1 + (long long)first * P::IN1 : nullptr;
+        e = pipe_stage_launch<P, 0>(o, i0, stride0, i1, sc, tickets ? tickets + 2 * c : nullptr, n, gravity, stream);
+        if (e == cudaSuccess)
+            e = pipe_stage_launch<P, 1>(o, i0, stride0, i1, sc, tickets ? tickets + 2 * c + 1 : nullptr, n, gravity, stream);
+    }
     if (scratch) {
         cudaError_t e2 = cudaFreeAsync(scratch, stream);
         if (e == cudaSuccess) e = e2;

@@ -485,7 +485,7 @@ def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead
 
 
 def emit_pipe_struct(pv: PipeVariant, min_blocks: Tuple[int, int] = (1, 1), warps: int = 8,
-                     sync_every: int = 256, scratch_lead: int = 160) -> Tuple[str, Dict[str, object]]:
+                     sync_every: int = 256, scratch_lead: int = 160, chunk_states: int = 0) -> Tuple[str, Dict[str, object]]:
     """min_blocks: resident CTAs per SM the two stage kernels are compiled for (register cap =
     65536 / (32 * warps * min_blocks)); warps: tiles (warps) per CTA."""
     max_run = max([len(offs) * ln for t in pv.tasks for (offs, ln) in t.runs] + [1])
@@ -501,7 +501,8 @@ def emit_pipe_struct(pv: PipeVariant, min_blocks: Tuple[int, int] = (1, 1), warp
            "    static constexpr int NTASKS0 = %d, NTASKS1 = %d, MINB0 = %d, MINB1 = %d, WARPS = %d;" % (
                len(pv.stage_tasks[0]), len(pv.stage_tasks[1]), min_blocks[0], min_blocks[1], warps),
            "    static constexpr long long TRACED_FLOPS = %d;" % pv.flops,
-           "    static constexpr int SYNC_EVERY = %d;" % (sync_every if warps > 1 else 0)]
+           "    static constexpr int SYNC_EVERY = %d;" % (sync_every if warps > 1 else 0),
+           "    static constexpr int CHUNK_STATES = %d;" % chunk_states]
     for s in (0, 1):
         for ti, t in enumerate(pv.stage_tasks[s]):
             txt += emit_task(t, "s%d_t%d" % (s, ti), pv.out, stage_pad, sync_every=sync_every if warps > 1 else 0,
