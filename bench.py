@@ -315,9 +315,11 @@ def run_b200_arm(a):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic, traffic_src = None, None
-    if (a.robot, a.alg, a.batch) == (ROBOT, ALG, BATCH):
-        try:        # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_final_tps_fdgrad_traffic.json")))
+    traffic_file = {("iiwa14", "fd_grad", 65536): "r1_final_tps_fdgrad_traffic.json",
+                    ("atlas", "fd_grad", 65536): "r1_final_pipe_fdgrad_atlas_traffic.json"}.get((a.robot, a.alg, a.batch))
+    if traffic_file:
+        try:        # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this step's kernels
+            tj = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))
             traffic, traffic_src = tj["traffic"], tj["source"]
         except (OSError, ValueError, KeyError):
             pass

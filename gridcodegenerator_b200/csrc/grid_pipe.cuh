@@ -162,7 +162,7 @@ pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stri
         // The task programs contain CTA-wide barriers (they keep the warps of the CTA on the same
         // lines of the program), so a warp past the last tile cannot sit out: it recomputes the
         // last tile and stores nothing (its scratch writes duplicate the owner's values).
-        const int my_tile = blk * P::WARPS + warp;
+        const int my_tile = blk * (int)(blockDim.x >> 5) + warp;
         const bool owner = my_tile < ntiles;
         const int tile = owner ? my_tile : ntiles - 1;
         const long long first = (long long)tile * 32;
@@ -187,6 +187,9 @@ pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stri
     }
 }
 
+// Warps per CTA are a launch-time choice (the kernel is compiled for up to P::WARPS): 8 when there is
+// enough work, fewer for mid-size batches so that the (task, tiles) items still cover every SM
+// (Atlas FD gradient at 8 192 states: 3 x 32 items of 8 tiles would occupy 96 of 148 SMs).
 template <class P, int STAGE>
 cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, const float *d_in1, float *scratch,
                               unsigned int *ticket, int num_states, float gravity, cudaStream_t stream) {
@@ -194,25 +197,41 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
     constexpr int ntasks = STAGE == 0 ? P::NTASKS0 : P::NTASKS1;
     if (ntasks == 0) return cudaSuccess;
     auto kern = pipe_kernel<P, STAGE>;
-    constexpr size_t smem_bytes = sizeof(float) * S::smem_words(STAGE) * P::WARPS;
-    static int cap = 0;                          // resident CTAs on this device (benign race: idempotent)
-    if (cap == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    constexpr size_t warp_smem = sizeof(float) * S::smem_words(STAGE);
+    static int sms = 0, per_sm[4] = {0, 0, 0, 0};          // resident CTAs per SM for 1, 2, 4, 8 warps (benign race)
+    if (sms == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(warp_smem * P::WARPS));
         if (e != cudaSuccess) return e;
-        int dev = 0, sms = 0, per_sm = 0;
+        int dev = 0, n = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * P::WARPS, smem_bytes);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-        cap = sms * per_sm;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        for (int i = 0; i < 4; i++) {
+            const int w = 1 << i;
+            if (w > P::WARPS) break;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[i], kern, 32 * w, warp_smem * w);
+            if (e != cudaSuccess) return e;
+        }
+        if (per_sm[0] < 1) return cudaErrorLaunchOutOfResources;
+        sms = n;
     }
     const int ntiles = (num_states + 31) / 32;
-    const int nblk = (ntiles + P::WARPS - 1) / P::WARPS;
+    // largest CTA whose items still give every resident CTA slot at least two items, else the smallest
+    int wi = 0;
+    for (int i = 3; i >= 0; i--) {
+        const int w = 1 << i;
+        if (w > P::WARPS || per_sm[i] < 1) continue;
+        wi = i;
+        const long long items_w = (long long)ntasks * ((ntiles + w - 1) / w);
+        if (items_w >= 2LL * sms * per_sm[i]) break;
+    }
+    const int w = 1 << wi;
+    const int nblk = (ntiles + w - 1) / w;
     const long long items = (long long)ntasks * nblk;
+    const long long cap = (long long)sms * per_sm[wi];
     const int blocks = (int)(items < cap ? items : cap);
-    kern<<<blocks, 32 * P::WARPS, smem_bytes, stream>>>(d_out, d_in0, stride0, d_in1, scratch,
-                                                        ticket, num_states, ntiles, nblk, gravity);
+    kern<<<blocks, 32 * w, warp_smem * w, stream>>>(d_out, d_in0, stride0, d_in1, scratch,
+                                                    items > cap ? ticket : nullptr, num_states, ntiles, nblk, gravity);
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -419,7 +438,8 @@ cudaError_t pipe_launch(float *d_out, const float *d_in0, int stride0, const flo
     constexpr int max_tasks = P::NTASKS0 > P::NTASKS1 ? P::NTASKS0 : P::NTASKS1;
     const long long max_items = (long long)max_tasks * (((chunk + 31) / 32 + P::WARPS - 1) / P::WARPS);
     // (the counters cost a memset node: ~1.5 us, visible on 10 us launches such as HyQ Minv at 16 384
-    // states - only worth it when every CTA takes several items)
+    // states - only worth it when every CTA takes several items; the stage launcher ignores them when
+    // every item has its own CTA)
     const bool use_tickets = max_items > 4LL * sms;
     const size_t tk_bytes = use_tickets ? ((size_t)nchunks * 2 * sizeof(unsigned int) + 255) / 256 * 256 : 0;
     const size_t sc_bytes = (size_t)((chunk + 31) / 32) * P::SCRATCH_WORDS * 32 * sizeof(float);

@@ -216,6 +216,34 @@ def test_host_path_grid_data_atlas_phase_split():
     data.close()
 
 
+def test_phase_split_chunked_launches_subprocess(tmp_path):
+    """GRID_PIPE_CHUNK (read once per process) cuts a batch into chunks that reuse one scratch array;
+    ragged last chunk and ragged last tile included.  Same bits as the unchunked launch."""
+    import subprocess
+    import sys
+    robot = load_named_robot("atlas")
+    eng = get_engine(robot)
+    N = 10007
+    q, qd, u, _ = make_states(robot.n, N, 41)
+    ref = run_alg(eng, "fd_grad", q, qd, u)
+    np.save(tmp_path / "ref.npy", ref)
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from gridcodegenerator_b200 import load_named_robot\n"
+        "from gridcodegenerator_b200.runtime import get_engine\n"
+        "from gridcodegenerator_b200.synthetic import make_states, pack_q_qd_u\n"
+        "r = load_named_robot('atlas'); e = get_engine(r)\n"
+        "q, qd, u, _ = make_states(r.n, %d, 41)\n"
+        "x = torch.from_numpy(pack_q_qd_u(q, qd, u)).cuda(); o = torch.empty(%d, 2 * r.n * r.n, device='cuda')\n"
+        "e.forward_dynamics_gradient_device(o, x); torch.cuda.synchronize()\n"
+        "assert np.array_equal(o.cpu().numpy(), np.load(%r)), 'chunked launch differs'\n"
+        "print('chunked ok')\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), N, N, str(tmp_path / "ref.npy")))
+    env = dict(os.environ, GRID_PIPE_CHUNK="4096", GRID_FORCE_KERNEL="pipe")
+    p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "chunked ok" in p.stdout, p.stdout + p.stderr
+
+
 def test_phase_split_concurrent_streams():
     """Two streams, two batches, launches interleaved: results equal the serial ones (the scratch
     arrays are per call)."""
