@@ -559,9 +559,13 @@ class KernelPlan:
                     self.pipe[pv.variant] = pv
                 self.kind[a] = "pipe" if self.kind[a] == "none" else self.kind[a] + "+pipe"
         self.cps_lanes = 16 if 2 * robot.n <= 16 else 32
-        # with phase-split kernels available the latency kernels only win for small batches
-        # (HyQ FD gradient: cps 10.7 / 16.8 us vs pipe 10.8 / 12.8 us at N = 512 / 2048)
-        self.cps_max_states = min(cps_max_states, 512) if self.pipe else cps_max_states
+        # where phase-split kernels exist they are at least as fast as the latency kernels at every batch
+        # size once their CTA size follows the batch (HyQ FD gradient N = 128: 8.6 vs 10.6 us, N = 512: 9.5
+        # vs 10.6 us, profiles/r1_matrix_final_all_robots.jsonl): no latency kernels for those algorithms
+        for a in ("id_grad", "fd_grad"):
+            if "pipe" in self.kind[a] and "+cps" in self.kind[a]:
+                self.kind[a] = self.kind[a].replace("+cps", "")
+        self.cps_max_states = cps_max_states
         # resident single-warp CTAs per SM = register cap 65536/(32*min_blocks).  Measured on B200
         # (profiles/r1_sweep_tps.md): the gradient programs spill at 128/168 registers and run
         # 2.1x faster at 255 registers with no spills; the small programs fit 128.
