@@ -291,8 +291,11 @@ def run_b200_arm(a):
     if rank == 0:
         small_in, small_out = ins[0][:128], outs[0][:128]
         us = eng.time_launches(a.alg, small_out, small_in, num_timesteps=128, stride=3 * n, reps=500)
+        floor = eng.time_launches("noop", small_out, small_in, num_timesteps=128, stride=3 * n, reps=500)
         lat = {"p50_us": float(np.percentile(us, 50)), "p90_us": float(np.percentile(us, 90)),
                "min_us": float(us.min()), "kernel": eng.kernel_kind(a.alg),
+               "floor_p50_us": float(np.percentile(floor, 50)),
+               "floor_what": "same event-pair method around an empty kernel: what the measurement itself costs",
                "what": "%s N=128, one CUDA event pair per launch recorded in C (grid_time_launches), 500 launches "
                        "queued back to back" % a.alg}
 

@@ -198,34 +198,40 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
     if (ntasks == 0) return cudaSuccess;
     auto kern = pipe_kernel<P, STAGE>;
     constexpr size_t warp_smem = sizeof(float) * S::smem_words(STAGE);
-    static int sms = 0, per_sm[4] = {0, 0, 0, 0};          // resident CTAs per SM for 1, 2, 4, 8 warps (benign race)
+    // candidate CTA sizes: 1, 2, 4, 8 warps and the size the kernel was compiled for
+    constexpr int NOPT = 5;
+    static const int opt_w[NOPT] = {1, 2, 4, 8, P::WARPS};
+    static int sms = 0, per_sm[NOPT] = {0, 0, 0, 0, 0};     // resident CTAs per SM per option (benign race)
     if (sms == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(warp_smem * P::WARPS));
-        if (e != cudaSuccess) return e;
-        int dev = 0, n = 0;
+        int dev = 0, n = 0, smem_max = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        for (int i = 0; i < 4; i++) {
-            const int w = 1 << i;
-            if (w > P::WARPS) break;
+        cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        size_t want = warp_smem * P::WARPS;
+        if (want > (size_t)smem_max) want = (size_t)smem_max / warp_smem * warp_smem;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+        if (e != cudaSuccess) return e;
+        for (int i = 0; i < NOPT; i++) {
+            const int w = opt_w[i];
+            if (w > P::WARPS || (i < NOPT - 1 && w == P::WARPS)) continue;      // too big / listed last
+            if (warp_smem * w > want) continue;                                    // staging does not fit
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[i], kern, 32 * w, warp_smem * w);
             if (e != cudaSuccess) return e;
         }
-        if (per_sm[0] < 1) return cudaErrorLaunchOutOfResources;
+        if (per_sm[NOPT - 1] < 1 && per_sm[0] < 1) return cudaErrorLaunchOutOfResources;
         sms = n;
     }
     const int ntiles = (num_states + 31) / 32;
     // largest CTA whose items still give every resident CTA slot at least two items, else the smallest
-    int wi = 0;
-    for (int i = 3; i >= 0; i--) {
-        const int w = 1 << i;
-        if (w > P::WARPS || per_sm[i] < 1) continue;
+    int wi = -1;
+    for (int i = NOPT - 1; i >= 0; i--) {
+        if (per_sm[i] < 1) continue;
         wi = i;
-        const long long items_w = (long long)ntasks * ((ntiles + w - 1) / w);
+        const long long items_w = (long long)ntasks * ((ntiles + opt_w[i] - 1) / opt_w[i]);
         if (items_w >= 2LL * sms * per_sm[i]) break;
     }
-    const int w = 1 << wi;
+    if (wi < 0) return cudaErrorLaunchOutOfResources;
+    const int w = opt_w[wi];
     const int nblk = (ntiles + w - 1) / w;
     const long long items = (long long)ntasks * nblk;
     const long long cap = (long long)sms * per_sm[wi];

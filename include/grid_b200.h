@@ -106,7 +106,8 @@ double grid_measure_fp32_tflops(int repeats);
 /* Times `reps` back-to-back launches of one algorithm ("id","minv","fd","id_grad","fd_grad", inputs
  * as for the matching *_device call with d_qdd = d_Minv = NULL) with one CUDA event pair per launch,
  * recorded from C so that no interpreter time sits between the events; h_us receives the `reps`
- * per-launch durations in microseconds.  This is how the N = 128 latency is measured. */
+ * per-launch durations in microseconds.  This is how the N = 128 latency is measured.  alg = "noop" times an
+ * empty kernel the same way: the floor of the method (event pair + launch), reported beside the latency. */
 int grid_time_launches(const char *alg, float *d_out, const float *d_in, int stride, int num_timesteps,
                        float gravity, int reps, float *h_us);
 /* Number of kernels this library has launched since load (the bench's gpu_launches). */
