@@ -361,3 +361,17 @@ def test_repeated_launches_are_bit_identical(name, family, monkeypatch):
     first = run_alg(eng, "fd_grad", q, qd, u)
     for _ in range(4):
         assert np.array_equal(run_alg(eng, "fd_grad", q, qd, u), first)
+
+
+def test_randomised_sweep_all_families(monkeypatch, capsys):
+    """tools/fuzz_parity.py: random batch sizes, strides, seeds, qdd overloads and kernel families (incl.
+    both launch modes of the phase-split kernels) against the C oracle, guard rows around every output."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(root, "tools", "fuzz_parity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr("sys.argv", ["fuzz_parity.py", "48"])
+    monkeypatch.setenv("GRID_FORCE_KERNEL", "tps")      # restored by monkeypatch after the sweep rewrites it
+    monkeypatch.setenv("GRID_PIPE_MODE", "staged")
+    assert mod.main() == 0, capsys.readouterr().out[-2000:]
