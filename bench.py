@@ -131,6 +131,44 @@ def reference_gpu_arm(robot_name, alg, N, host_in):
     return out
 
 
+def other_baseline_configs():
+    """The other BASELINE.json configurations, timed in the same run (C-side event pairs, 20 launches each,
+    buffers reused: L2-resident outputs) - context for the headline line, not part of its timed region."""
+    import torch
+    from gridcodegenerator_b200 import load_named_robot
+    from gridcodegenerator_b200.algorithms import algorithmic_flops
+    from gridcodegenerator_b200.runtime import get_engine
+    from gridcodegenerator_b200.synthetic import make_states, pack_q_qd_u, seed_for
+    out = {}
+    cases = [("cfg3_hyq_N16384", "hyq", ("id", "minv", "fd"), 16384),
+             ("cfg4_atlas_N65536", "atlas", ("fd_grad",), 65536),
+             ("cfg4_atlas_N8192_per_gpu_of_8", "atlas", ("fd_grad",), 8192),
+             ("cfg5_chain64_N65536", "chain64", ("id",), 65536),
+             ("cfg5_chain64_N4096", "chain64", ("fd_grad",), 4096)]
+    for key, name, algs, N in cases:
+        try:
+            robot = load_named_robot(name)
+            eng = get_engine(robot)
+            n = robot.n
+            q, qd, u, _ = make_states(n, N, seed_for(name))
+            x = torch.from_numpy(pack_q_qd_u(q, qd, u)).cuda()
+            res = {}
+            for alg in algs:
+                words = {"id": n, "minv": n * n, "fd": n, "id_grad": 2 * n * n, "fd_grad": 2 * n * n}[alg]
+                o = torch.empty(N, words, device="cuda")
+                us = eng.time_launches(alg, o, x, reps=20)
+                p50 = float(np.median(us))
+                res[alg] = {"p50_us": p50, "evals_per_s": N / p50 * 1e6, "kernel": eng.kernel_kind(alg),
+                            "algorithmic_tflops": algorithmic_flops(robot)[alg] * N / p50 / 1e6}
+                del o
+            out[key] = res
+            del x
+            torch.cuda.empty_cache()
+        except Exception as e:                       # never let the context runs break the headline line
+            out[key] = {"unavailable": str(e)[:200]}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # clocks sampler
 # ---------------------------------------------------------------------------------------------
@@ -356,6 +394,8 @@ def run_b200_arm(a):
     }
 
     line["reference_gpu"] = reference_gpu_arm(a.robot, a.alg, N, host_in)
+    if world == 1 and (a.robot, a.alg, a.batch) == (ROBOT, ALG, BATCH):
+        line["other_configs"] = other_baseline_configs()
 
     if not a.no_cpu_baseline:
         import multiprocessing as mp
