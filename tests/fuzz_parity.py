@@ -2,7 +2,7 @@
 """Randomised parity sweep: random batch sizes, seeds, strides and kernel families against the float64
 C oracle (pinned to the reference's outputs).  Prints one JSON line per case and a summary; exit 1 on any
 tolerance violation.
-  python tools/fuzz_parity.py [cases]
+  python tests/fuzz_parity.py [cases]
 """
 import json
 import os

@@ -364,11 +364,11 @@ def test_repeated_launches_are_bit_identical(name, family, monkeypatch):
 
 
 def test_randomised_sweep_all_families(monkeypatch, capsys):
-    """tools/fuzz_parity.py: random batch sizes, strides, seeds, qdd overloads and kernel families (incl.
+    """tests/fuzz_parity.py: random batch sizes, strides, seeds, qdd overloads and kernel families (incl.
     both launch modes of the phase-split kernels) against the C oracle, guard rows around every output."""
     import importlib.util
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(root, "tools", "fuzz_parity.py"))
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(root, "tests", "fuzz_parity.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     monkeypatch.setattr("sys.argv", ["fuzz_parity.py", "48"])

@@ -2,8 +2,8 @@
 """Times (robot, algorithm, batch, kernel family) combinations with CUDA events; JSON lines out.
   python tools/bench_matrix.py iiwa14:fd_grad:128:wps iiwa14:fd_grad:128:tps atlas:fd_grad:65536:auto ...
 A robot name may carry a library tag (iiwa14@_pipe16: an experimental build made beforehand with
-build_robot_library(..., tag="_pipe16")).  Every line also reports the FP32 error of the first
-states against the float64 C oracle.
+build_robot_library(..., tag="_pipe16")).  Timing only: parity lives in tests/ (tests/parity_report.py,
+tests/fuzz_parity.py).
 """
 import json
 import os
@@ -18,7 +18,6 @@ from gridcodegenerator_b200 import load_named_robot                      # noqa:
 from gridcodegenerator_b200.algorithms import algorithmic_flops         # noqa: E402
 from gridcodegenerator_b200.runtime import get_engine                    # noqa: E402
 from gridcodegenerator_b200.synthetic import make_states, pack_q_qd_u    # noqa: E402
-from oracle import c_oracle as C                                         # noqa: E402
 
 
 def main():
@@ -49,13 +48,8 @@ def main():
         us = eng.time_launches(alg, out, x, reps=reps)      # event pairs recorded in C, launches queued back to back
         p50 = float(np.median(us))
         fl = algorithmic_flops(robot)[alg]
-        M = min(N, 2048)
-        q64, qd64, u64 = (a[:M].astype(np.float64) for a in (q, qd, u))
-        ref = C.batch(robot, alg, q64, qd64, u64 if alg in ("fd", "fd_grad") else None)
-        o = out[:M].cpu().numpy().astype(np.float64)
         print(json.dumps({"spec": spec, "p50_us": p50, "min_us": float(us.min()), "evals_per_s": N / p50 * 1e6,
-                          "alg_tflops": fl * N / p50 / 1e6,
-                          "rel_err": float(np.abs(o - ref).max() / np.abs(ref).max())}), flush=True)
+                          "alg_tflops": fl * N / p50 / 1e6}), flush=True)
 
 
 if __name__ == "__main__":
