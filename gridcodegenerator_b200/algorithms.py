@@ -161,7 +161,7 @@ def cross_force(v: Sequence[V], f: Sequence[V]) -> List[V]:
 
 # ---- RNEA -------------------------------------------------------------------------
 class RneaResult:
-    __slots__ = ("c", "v", "a", "f", "Xa", "Iv")
+    __slots__ = ("c", "v", "a", "f", "Xa", "Iv", "f_fpass")
 
 
 def rnea(sr: SymRobot, qd: Sequence[V], qdd: Optional[Sequence[V]], gravity: V) -> RneaResult:
@@ -187,6 +187,7 @@ def rnea(sr: SymRobot, qd: Sequence[V], qdd: Optional[Sequence[V]], gravity: V) 
             a[i] = vadd(a[i], cross_motion_axis(p, k, v[i], qd[i]))
         Iv[i] = sr.I_mul(i, v[i])
         f[i] = vadd(sr.I_mul(i, a[i]), cross_force(v[i], Iv[i]))
+    f_fpass = [list(x) for x in f]            # forces before the backward accumulation (_test.py:5-76)
     c = [None] * n
     for i in range(n - 1, -1, -1):
         c[i] = f[i][robot.S_ind[i]] + qd[i] * robot.damping[i]
@@ -194,13 +195,15 @@ def rnea(sr: SymRobot, qd: Sequence[V], qdd: Optional[Sequence[V]], gravity: V) 
         if par >= 0:
             f[par] = vadd(f[par], sr.XT_force(i, f[i]))
     res = RneaResult()
-    res.c, res.v, res.a, res.f, res.Xa, res.Iv = c, v, a, f, Xa, Iv
+    res.c, res.v, res.a, res.f, res.Xa, res.Iv, res.f_fpass = c, v, a, f, Xa, Iv, f_fpass
     return res
 
 
 # ---- Minv ---------------------------------------------------------------------------
-def minv(sr: SymRobot) -> Dict[Tuple[int, int], V]:
-    """Upper-triangular M^-1 as {(row, col): V}, col >= row."""
+def minv(sr: SymRobot, bpass: Optional[dict] = None) -> Dict[Tuple[int, int], V]:
+    """Upper-triangular M^-1 as {(row, col): V}, col >= row.  `bpass` (a dict) receives the state
+    after the backward pass - Minv entries, F columns, U, Dinv - i.e. what the reference's
+    test_minv_bpass returns (_test.py:117-184)."""
     p, robot, n = sr.p, sr.robot, sr.n
     zero6 = lambda: zeros(p, 6)
     Mi: Dict[Tuple[int, int], V] = {}
@@ -229,6 +232,8 @@ def minv(sr: SymRobot) -> Dict[Tuple[int, int], V]:
                     Ia[c][r] = Ia[r][c]
             Ip = sr.congruence(i, Ia)
             IA[par] = [[IA[par][r][c] + Ip[r][c] for c in range(6)] for r in range(6)]
+    if bpass is not None:
+        bpass.update(Minv=dict(Mi), F=[dict(Fi) for Fi in F], U=list(U), Dinv=list(Dinv))
     for i in range(n):
         k, par = robot.S_ind[i], robot.parent[i]
         cols = range(i, n)
@@ -273,13 +278,15 @@ class _DirectSource:
         return cross_motion_axis(self.p, self.robot.S_ind[i], self.R.f[i])
 
 
-def rnea_grad_columns(sr: SymRobot, qd: Sequence[V], R: Optional[RneaResult], src=None, joints=None):
+def rnea_grad_columns(sr: SymRobot, qd: Sequence[V], R: Optional[RneaResult], src=None, joints=None, record=None):
     """Yields (j, dc_dq_col, dc_dqd_col) one du-column pair at a time; each col is a
     dict {row i: V} over anc(j) | sub(j) (structural zeros elsewhere).  Columns are
     independent through both passes, which is what lets the emitter finish and store
     one column before starting the next.  `src` (default: the RNEA result itself) is where
     the per-joint state data v, I v, mxS(X a_parent), mxS(f) come from; `joints` restricts
-    the columns (pipeline.py traces one group of columns per program)."""
+    the columns (pipeline.py traces one group of columns per program).  `record(j, name, i, s, vec)`
+    is called with the per-joint intermediates of column j (names "dv", "da", "df_fp", "df": the arrays
+    the reference's test_rnea_grad_inner returns, _test.py:229-488)."""
     p, robot, n = sr.p, sr.robot, sr.n
     if src is None:
         src = _DirectSource(p, robot, R)
@@ -307,11 +314,17 @@ def rnea_grad_columns(sr: SymRobot, qd: Sequence[V], R: Optional[RneaResult], sr
             for s in (0, 1):
                 df[s][i] = vadd(vadd(sr.I_mul(i, da[s][i]), cross_force(dv[s][i], Ivi)),
                                 cross_force(vi, sr.I_mul(i, dv[s][i])))
+                if record is not None:
+                    record(j, "dv", i, s, dv[s][i])
+                    record(j, "da", i, s, da[s][i])
+                    record(j, "df_fp", i, s, df[s][i])
         cols = ({}, {})
         for i in reversed(sub):
             par = robot.parent[i]
             for s in (0, 1):
                 cols[s][i] = df[s][i][robot.S_ind[i]]
+                if record is not None:
+                    record(j, "df", i, s, df[s][i])
             if i != j:
                 for s in (0, 1):
                     df[s][par] = vadd(df[s][par], sr.XT_force(i, df[s][i]))
@@ -323,6 +336,8 @@ def rnea_grad_columns(sr: SymRobot, qd: Sequence[V], R: Optional[RneaResult], sr
             i = robot.parent[i]
             for s in (0, 1):
                 cols[s][i] = up[s][robot.S_ind[i]]
+                if record is not None:
+                    record(j, "df", i, s, up[s])
         cols[1][j] = cols[1][j] + robot.damping[j]
         yield j, cols[0], cols[1]
 
@@ -414,6 +429,77 @@ def trace_fd_grad(robot: Robot, use_qdd_minv: bool = False) -> Program:
     return p
 
 
+# ---- consumers fused after the FD gradient ------------------------------------
+# The reference stops at writing df_du (2n^2 floats per state) to global memory and shipping it to
+# the host (algorithms/_forward_dynamics_gradient.py:159-161, 235-238).  Trajectory optimisers do
+# not want df_du itself but the explicit-Euler integrator Jacobians built from it,
+#     x = [q; qd],  x+ = x + dt [qd; qdd(q, qd, u)]
+#     A = dx+/dx = [[I, dt I], [dt dqdd/dq, I + dt dqdd/dqd]],   B = dx+/du = [[0], [dt Minv]],
+# or only their action on a costate.  Both are traced here INTO the gradient program, so the
+# gradient never leaves the registers of the thread that computed it.
+#   "fd_vjp": inputs (q, qd, u), lam = [lam_q; lam_v] (2n), dt
+#             out[5n] = [x+ (2n) | A^T lam (2n) | B^T lam (n)]            -- O(n) words per state
+#             A^T lam = [lam_q + dt (dqdd/dq)^T lam_v ; lam_v + dt lam_q + dt (dqdd/dqd)^T lam_v]
+#             with (df_du)^T lam_v = -dc_du^T (Minv lam_v): Minv is applied ONCE (n^2), not per column
+#   "fd_lin": inputs (q, qd, u), dt
+#             out[2n + 3n^2] = [x+ (2n) | A21 = dt dqdd/dq | A22 = I + dt dqdd/dqd | B2 = dt Minv],
+#             the three n x n blocks column-major (B2 full symmetric): the non-constant blocks of A, B
+def consumer_out_words(alg: str, n: int) -> int:
+    return {"fd_vjp": 5 * n, "fd_lin": 2 * n + 3 * n * n}[alg]
+
+
+def vjp_column(p: Program, cq: Dict[int, V], cqd: Dict[int, V], w: Sequence[V], lam_q_j: V, lam_v_j: V, dt: V):
+    """(A^T lam)[j], (A^T lam)[n + j] from the dc_du columns of joint j and w = Minv lam_v."""
+    rows = sorted(cq)
+    gq = dot([cq[r] for r in rows], [w[r] for r in rows])
+    rows = sorted(cqd)
+    gqd = dot([cqd[r] for r in rows], [w[r] for r in rows])
+    return lam_q_j - dt * gq, lam_v_j + dt * (lam_q_j - gqd)
+
+
+def trace_fd_consumer(robot: Robot, alg: str) -> Program:
+    """Thread-per-state program of a fused consumer ("fd_vjp" or "fd_lin")."""
+    p = Program()
+    n = robot.n
+    q, qd, u = _inputs(p, n, ("q", "qd", "u"))
+    g, dt = p.inp("gravity"), p.inp("dt")
+    sr = SymRobot(p, robot, q)
+    R0 = rnea(sr, qd, None, g)
+    Mi = minv(sr)
+    umc = [u[i] - R0.c[i] for i in range(n)]
+    qdd = [dot([minv_get(Mi, i, j) for j in range(n)], umc) for i in range(n)]
+    R = rnea(sr, qd, qdd, g)
+    for i in range(n):
+        p.output(alg, i, q[i] + dt * qd[i])
+        p.output(alg, n + i, qd[i] + dt * qdd[i])
+    if alg == "fd_vjp":
+        lam = [p.inp("lam%d" % i) for i in range(2 * n)]
+        w = [dot([minv_get(Mi, i, j) for j in range(n)], lam[n:]) for i in range(n)]
+        for j, cq, cqd in rnea_grad_columns(sr, qd, R):
+            aq, av = vjp_column(p, cq, cqd, w, lam[j], lam[n + j], dt)
+            p.output(alg, 2 * n + j, aq)
+            p.output(alg, 3 * n + j, av)
+        for i in range(n):
+            p.output(alg, 4 * n + i, dt * w[i])
+        return p
+    if alg != "fd_lin":
+        raise ValueError(alg)
+    base = 2 * n
+    for j, cq, cqd in rnea_grad_columns(sr, qd, R):
+        for s, col in ((0, cq), (1, cqd)):
+            rows = sorted(col)
+            scaled = [col[r] * dt for r in rows]
+            for i in range(n):
+                v = -dot([minv_get(Mi, i, r) for r in rows], scaled)
+                if s == 1 and i == j:
+                    v = v + 1.0
+                p.output(alg, base + s * n * n + n * j + i, v)
+    for j in range(n):
+        for i in range(n):
+            p.output(alg, base + 2 * n * n + n * j + i, dt * minv_get(Mi, i, j))
+    return p
+
+
 # ---- extra traces used by the emitted header's _inner functions and the facade's test_* methods ----
 def trace_id_full(robot: Robot, use_qdd: bool = False) -> Program:
     """c plus the reference's s_vaf block [v(6n) | a(6n) | f(6n)]."""
@@ -430,6 +516,86 @@ def trace_id_full(robot: Robot, use_qdd: bool = False) -> Program:
             p.output("vaf", 6 * i + r, R.v[i][r])
             p.output("vaf", 6 * n + 6 * i + r, R.a[i][r])
             p.output("vaf", 12 * n + 6 * i + r, R.f[i][r])
+    return p
+
+
+def trace_rnea_fpass(robot: Robot, use_qdd: bool = False) -> Program:
+    """(v, a, f) after the forward pass only - the reference's test_rnea_fpass (_test.py:5-76):
+    output "vaf" = [v(6n) | a(6n) | f before the backward accumulation (6n)], joint-major."""
+    p = Program()
+    n = robot.n
+    q, qd = _inputs(p, n, ("q", "qd"))
+    qdd = _inputs(p, n, ("qdd",))[0] if use_qdd else None
+    R = rnea(SymRobot(p, robot, q), qd, qdd, p.inp("gravity"))
+    for i in range(n):
+        for r in range(6):
+            p.output("vaf", 6 * i + r, R.v[i][r])
+            p.output("vaf", 6 * n + 6 * i + r, R.a[i][r])
+            p.output("vaf", 12 * n + 6 * i + r, R.f_fpass[i][r])
+    return p
+
+
+def trace_minv_bpass(robot: Robot) -> Program:
+    """State after the backward pass of the Minv algorithm - the reference's test_minv_bpass
+    (_test.py:117-184): outputs "Minv" (n*n, row-major [row][col]; only the entries the pass writes:
+    col in subtree(row)), "F" (n*6*n, [joint][row][col]), "U" (n*6), "Dinv" (n); everything the
+    reference leaves at zero is a constant 0 here."""
+    p = Program()
+    n = robot.n
+    (q,) = _inputs(p, n, ("q",))
+    snap: dict = {}
+    minv(SymRobot(p, robot, q), bpass=snap)
+    for i in range(n):
+        for j in range(n):
+            p.output("Minv", i * n + j, snap["Minv"].get((i, j), 0.0))
+            Fij = snap["F"][i].get(j)
+            for r in range(6):
+                p.output("F", (i * 6 + r) * n + j, Fij[r] if Fij is not None else 0.0)
+        for r in range(6):
+            p.output("U", i * 6 + r, snap["U"][i][r])
+        p.output("Dinv", i, snap["Dinv"][i])
+    return p
+
+
+GRAD_INNER_ARRAYS = ("dv_dq", "dv_dqd", "da_dq", "da_dqd", "df_fp_dq", "df_fp_dqd", "df_dq", "df_dqd")
+
+
+def trace_id_grad_inner(robot: Robot) -> Program:
+    """Everything the reference's test_rnea_grad_inner returns (_test.py:229-488) from (q, qd, v, a, f):
+    "dc_du" plus the eight 6 x n x n arrays of GRAD_INNER_ARRAYS, flat [row][col][joint]
+    (d<x>_joint / du_col); entries outside the ancestor/subtree structure are constant zeros."""
+    p = Program()
+    n = robot.n
+    q, qd = _inputs(p, n, ("q", "qd"))
+    sr = SymRobot(p, robot, q)
+    R = RneaResult()
+    R.v = [[p.inp("vaf%d" % (6 * i + r)) for r in range(6)] for i in range(n)]
+    R.a = [[p.inp("vaf%d" % (6 * n + 6 * i + r)) for r in range(6)] for i in range(n)]
+    R.f = [[p.inp("vaf%d" % (12 * n + 6 * i + r)) for r in range(6)] for i in range(n)]
+    R.Iv = [sr.I_mul(i, R.v[i]) for i in range(n)]
+    R.Xa = []
+    for i in range(n):
+        if robot.parent[i] >= 0:
+            R.Xa.append(vsub(R.a[i], cross_motion_axis(p, robot.S_ind[i], R.v[i], qd[i])))
+        else:
+            R.Xa.append(list(R.a[i]))
+    R.c = None
+    got: Dict[Tuple[str, int, int, int], V] = {}
+
+    def record(j, name, i, s, vec):
+        arr = "%s_%s" % (name, "dq" if s == 0 else "dqd")
+        for r in range(6):
+            got[(arr, r, j, i)] = vec[r]
+
+    for j, cq, cqd in rnea_grad_columns(sr, qd, R, record=record):
+        for i in range(n):
+            p.output("dc_du", n * j + i, cq.get(i, 0.0))
+            p.output("dc_du", n * n + n * j + i, cqd.get(i, 0.0))
+    for arr in GRAD_INNER_ARRAYS:
+        for r in range(6):
+            for j in range(n):
+                for i in range(n):
+                    p.output(arr, (r * n + j) * n + i, got.get((arr, r, j, i), 0.0))
     return p
 
 
@@ -684,6 +850,8 @@ TRACERS = {
     "id_grad_qdd": lambda robot: trace_id_grad(robot, True),
     "fd_grad": lambda robot: trace_fd_grad(robot, False),
     "fd_grad_qdd_minv": lambda robot: trace_fd_grad(robot, True),
+    "fd_vjp": lambda robot: trace_fd_consumer(robot, "fd_vjp"),
+    "fd_lin": lambda robot: trace_fd_consumer(robot, "fd_lin"),
 }
 
 # packed (float2) variants of the gradient programs

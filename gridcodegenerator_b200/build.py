@@ -14,7 +14,7 @@ import subprocess
 import time
 from typing import Dict, Optional, Tuple
 
-from .codegen import CODEGEN_VERSION, KernelPlan, generate_translation_unit
+from .codegen import CODEGEN_VERSION, KernelPlan, generate_translation_unit, plan_signature
 from .robot import Robot
 
 PKG = os.path.dirname(os.path.abspath(__file__))
@@ -53,8 +53,11 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found: the B200 kernels cannot be built (there is no CPU fallback)")
 
 
-def lib_path(robot: Robot, tag: str = "") -> str:
-    return os.path.join(LIB_DIR, "libgrid_%s_%s_%s%s.so" % (robot.name, robot.param_hash(), _static_hash(), tag))
+def lib_path(robot: Robot, tag: str = "", plan: Optional[KernelPlan] = None) -> str:
+    """<robot>_<robot hash>_<static hash>[_p<plan hash>][tag]: a non-default KernelPlan is part of the key."""
+    sig = plan_signature(plan)
+    return os.path.join(LIB_DIR, "libgrid_%s_%s_%s%s%s.so" % (robot.name, robot.param_hash(), _static_hash(),
+                                                             "_p" + sig if sig else "", tag))
 
 
 def build_robot_library(robot: Robot, plan: Optional[KernelPlan] = None, force: bool = False, tag: str = "",
@@ -62,21 +65,28 @@ def build_robot_library(robot: Robot, plan: Optional[KernelPlan] = None, force: 
     """Returns (path to .so, build info).  Rebuilds only when the cache key changed."""
     os.makedirs(GEN_DIR, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
-    so = lib_path(robot, tag)
+    so = lib_path(robot, tag, plan)
     info: Dict[str, dict] = {}
     if os.path.exists(so) and not force:
         return so, info
     t0 = time.time()
-    src, stats = generate_translation_unit(robot, plan, ns_tag=tag)
-    cu = os.path.join(GEN_DIR, "grid_%s_%s%s.cu" % (robot.name, robot.param_hash(), tag))
-    with open(cu, "w") as f:
+    sig = plan_signature(plan)
+    src, stats = generate_translation_unit(robot, plan, ns_tag=tag + ("_p" + sig if sig else ""))
+    cu = os.path.join(GEN_DIR, "grid_%s_%s%s%s.cu" % (robot.name, robot.param_hash(), "_p" + sig if sig else "", tag))
+    # concurrent builders (one rank per GPU) must not share a temporary: per-process names, atomic rename
+    cu_tmp = "%s.%d.tmp.cu" % (cu[:-3], os.getpid())
+    so_tmp = "%s.%d.tmp" % (so, os.getpid())
+    with open(cu_tmp, "w") as f:
         f.write(src)
+    os.replace(cu_tmp, cu)
     t1 = time.time()
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v", "-I", CSRC, "-I", INCLUDE, "-o", so + ".tmp", cu] + list(extra_flags)
+    cmd = [find_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v", "-I", CSRC, "-I", INCLUDE, "-o", so_tmp, cu] + list(extra_flags)
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
+        if os.path.exists(so_tmp):
+            os.remove(so_tmp)
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (cu, proc.stdout[-4000:], proc.stderr[-8000:]))
-    os.replace(so + ".tmp", so)
+    os.replace(so_tmp, so)
     # drop stale libraries of the same robot
     prefix = "libgrid_%s_" % robot.name
     keep = "_%s_%s" % (robot.param_hash(), _static_hash())

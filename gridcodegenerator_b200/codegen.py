@@ -32,9 +32,13 @@ VARIANTS = {
     "id_grad_qdd":      ("AlgIdGradQdd",    2, 1, 0, "dc_du", lambda n: 2 * n * n),
     "fd_grad":          ("AlgFdGrad",       3, 0, 0, "df_du", lambda n: 2 * n * n),
     "fd_grad_qdd_minv": ("AlgFdGradPre",    2, 1, 1, "df_du", lambda n: 2 * n * n),
+    # consumers fused after the FD gradient (algorithms.trace_fd_consumer); in1 = lam (2n words)
+    "fd_vjp":           ("AlgFdVjp",        3, 2, 0, "fd_vjp", lambda n: 5 * n),
+    "fd_lin":           ("AlgFdLin",        3, 0, 0, "fd_lin", lambda n: 2 * n + 3 * n * n),
 }
 
-_NAME_RE = re.compile(r"^(qdd|qd|q|u|Minv)(\d+)$")
+_NAME_RE = re.compile(r"^(qdd|qd|q|u|Minv|lam)(\d+)$")
+_SCALARS = ("gravity", "dt")
 
 
 def _flit(x: float) -> str:
@@ -77,13 +81,15 @@ def emit_eval(p: Program, n: int, in0_words: int, in1_words: int, out_name: str,
             return n + idx
         if kind == "u":
             return 2 * n + idx
-        if kind == "qdd":
+        if kind in ("qdd", "lam"):
             return in0_words + idx
         return in0_words + in1_words + idx        # Minv
 
     for i, k in enumerate(p.nodes):
-        if live[i] and k[0] == "in" and k[1] != "gravity":
+        if live[i] and k[0] == "in" and k[1] not in _SCALARS:
             lines.append("%sconst float t%d = s_in[%d];   // %s" % (indent, i, word_of(k[1]), k[1]))
+        elif live[i] and k[0] == "in":
+            lines.append("%sconst float t%d = %s;" % (indent, i, k[1]))
     lines.append(indent + "__syncwarp();")
     parks = getattr(p, "parks", {})
 
@@ -149,8 +155,7 @@ def emit_eval(p: Program, n: int, in0_words: int, in1_words: int, out_name: str,
         if sync_every and emitted % sync_every == 0:
             body.append(indent + "__syncthreads();")
         if op == "in":
-            if k[1] == "gravity":
-                body.append("%sconst float t%d = gravity;" % (indent, i))
+            pass                                   # loaded above (scalars included)
         elif op in ("sin", "cos"):
             a = k[1]
             if a not in sincos_done:
@@ -348,7 +353,8 @@ def emit_alg_struct_looped(robot: Robot, sname: str, alg: str, use_qdd: bool = F
            "    static constexpr int IN0 = %d, IN1 = %d, IN2 = 0, OUT = %d;" % (in0, in1, out_words),
            "    static constexpr long long TRACED_FLOPS = %d;   // %d once + %d columns x %d" % (
                cnt["flops"], cnt["flops"] - 2 * n * n_body, 2 * n, n_body),
-           "    static __device__ __forceinline__ void eval(const float *s_in, float *s_out, const float gravity) {"]
+           "    static __device__ __forceinline__ void eval(const float *s_in, float *s_out, const float gravity,"
+           " const float dt) {"]
     txt += pre
     txt.append(ind + "#pragma unroll 1")
     txt.append(ind + "for (int col = 0; col < %d; ++col) {" % (2 * n))
@@ -369,7 +375,8 @@ def emit_alg_struct(robot: Robot, variant: str, p: Optional[Program] = None,
            "    static constexpr int IN0 = %d, IN1 = %d, IN2 = %d, OUT = %d;" % (in0, in1, in2, out),
            "    static constexpr long long TRACED_FLOPS = %d;   // %d mul + %d add per state" % (
                cnt["flops"], cnt["mul"], cnt["add"]),
-           "    static __device__ __forceinline__ void eval(const float *s_in, float *s_out, const float gravity) {"]
+           "    static __device__ __forceinline__ void eval(const float *s_in, float *s_out, const float gravity,"
+           " const float dt) {"]
     txt += body
     txt += ["    }", "};", ""]
     return "\n".join(txt), cnt
@@ -512,6 +519,9 @@ class KernelPlan:
                  tps_pairs: bool = False, tps_v2_park=None, pipe_algs=None, pipe_min_states: int = 0,
                  pipe_opts: Optional[Dict[str, int]] = None, pipe_min_blocks: Tuple[int, int] = (1, 1),
                  pipe_warps: int = 8, pipe_sync_every: int = 256, pipe_scratch_lead: int = 160):
+        # every constructor argument except the robot: build.py hashes this into the library name, so
+        # a library built with one plan is never returned for another
+        self._args = {k: v for k, v in locals().items() if k not in ("self", "robot")}
         self.robot = robot
         self.tps_warps = tps_warps
         self.tps_sync_every = tps_sync_every if tps_warps > 1 else 0
@@ -558,6 +568,18 @@ class KernelPlan:
                 for pv in pvs:
                     self.pipe[pv.variant] = pv
                 self.kind[a] = "pipe" if self.kind[a] == "none" else self.kind[a] + "+pipe"
+        # consumers fused after the FD gradient ride on the family that serves fd_grad at large batches
+        self.consumers: Dict[str, str] = {}
+        for c in ("fd_vjp", "fd_lin"):
+            fams = []
+            if "tps" in self.kind["fd_grad"]:
+                fams.append("tps")
+            if "pipe" in self.kind["fd_grad"]:
+                pv = PipeVariant(robot, c, **self.pipe_opts)
+                if pv.feasible:
+                    self.pipe[c] = pv
+                    fams.append("pipe")
+            self.consumers[c] = "+".join(fams) if fams else "none"
         self.cps_lanes = 16 if 2 * robot.n <= 16 else 32
         # where phase-split kernels exist they are at least as fast as the latency kernels at every batch
         # size once their CTA size follows the batch (HyQ FD gradient N = 128: 8.6 vs 10.6 us, N = 512: 9.5
@@ -572,6 +594,19 @@ class KernelPlan:
         self.min_blocks = {"id": 16, "minv": 16, "fd": 16, "id_grad": 8, "fd_grad": 8}
         if tps_min_blocks:
             self.min_blocks.update(tps_min_blocks)
+
+
+def plan_signature(plan: Optional["KernelPlan"]) -> str:
+    """'' for the default plan, else a short hash of the plan's constructor arguments."""
+    if plan is None:
+        return ""
+    import hashlib
+    default = KernelPlan.__init__.__defaults__
+    names = KernelPlan.__init__.__code__.co_varnames[2:2 + len(default)]
+    args = {k: plan._args[k] for k in names}
+    if all(args[k] == d for k, d in zip(names, default)):
+        return ""
+    return hashlib.sha256(repr(sorted(args.items(), key=lambda kv: kv[0])).encode()).hexdigest()[:8]
 
 
 _LAUNCHERS = r'''
@@ -634,6 +669,11 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
             txt, cnt = emit_alg_struct(robot, v, p=prog, sync_every=plan.tps_sync_every)
             out.append(txt)
             stats[v] = cnt
+    for c, fam in plan.consumers.items():
+        if "tps" in fam:
+            txt, cnt = emit_alg_struct(robot, c, sync_every=plan.tps_sync_every)
+            out.append(txt)
+            stats[c] = cnt
     has_cps = any("cps" in k for k in plan.kind.values())
     if has_cps:
         for nm, alg, uq in (("ColIdGrad", "id_grad", False), ("ColIdGradQdd", "id_grad", True),
@@ -689,22 +729,23 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
         return lines
 
     L: List[str] = []
-    L.append("// batches up to WPS_MAX_STATES use the wide kernels when both families exist; the\n"
-             "// environment variable GRID_FORCE_KERNEL=tps|wps overrides (tests exercise both).\n"
+    L.append("// Kernel-family choice.  The override comes from options() (environment read once at first use,\n"
+             "// grid_set_option() afterwards): no getenv on the launch path.\n"
+             "// batches up to WPS_MAX_STATES use the wide kernels when both families exist\n"
              "static bool use_wide(int N) {\n"
-             "    const char *f = getenv(\"GRID_FORCE_KERNEL\");\n"
-             "    if (f && !strcmp(f, \"wps\")) return true;\n"
-             "    if (f && !strcmp(f, \"tps\")) return false;\n"
+             "    const int f = options().force_kernel;\n"
+             "    if (f == kWps) return true;\n"
+             "    if (f == kTps) return false;\n"
              "    return N <= %d;\n}" % plan.wps_max_states)
     L.append("// small batches go to the lane-per-column latency kernels\n"
              "static bool use_cps(int N) {\n"
-             "    const char *f = getenv(\"GRID_FORCE_KERNEL\");\n"
-             "    if (f) return !strcmp(f, \"cps\");\n"
+             "    const int f = options().force_kernel;\n"
+             "    if (f != kAuto) return f == kCps;\n"
              "    return N <= %d;\n}" % plan.cps_max_states)
     L.append("// large batches of robots with phase-split kernels (grid_pipe.cuh)\n"
              "static bool use_pipe(int N) {\n"
-             "    const char *f = getenv(\"GRID_FORCE_KERNEL\");\n"
-             "    if (f) return !strcmp(f, \"pipe\");\n"
+             "    const int f = options().force_kernel;\n"
+             "    if (f != kAuto) return f == kPipe;\n"
              "    return N >= %d;\n}" % plan.pipe_min_states)
     G = plan.cps_lanes
     PL = lambda struct, out, inp, in1: "pipe::pipe_launch<gen::%s>(%s, %s, stride, %s, N, g, s)" % (struct, out, inp, in1)
@@ -748,10 +789,33 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
               pipe_call=[("!d_qdd", PL("PipeFdGrad", "d_df_du", "d_in", "nullptr"))])
     L.append("}")
 
-    kinds = "\n".join('    if (!strcmp(alg, "%s")) return "%s";' % (a, k) for a, k in plan.kind.items())
+    for c, struct, pstruct, lam in (("fd_vjp", "AlgFdVjp", "PipeFdVjp", "d_lam"), ("fd_lin", "AlgFdLin", "PipeFdLin", "nullptr")):
+        fam = plan.consumers[c]
+        sig = "float *d_out, const float *d_in, int stride, %sint N, float g, float dt, cudaStream_t s" % (
+            "const float *d_lam, " if c == "fd_vjp" else "")
+        L.append("cudaError_t launch_%s(%s) {" % (c, sig))
+        pipe_call = "pipe::pipe_launch<gen::%s>(d_out, d_in, stride, %s, N, g, s, dt)" % (pstruct, lam)
+        tps_call = "tps_launch<%s, %d, %d>(d_out, d_in, stride, %s, nullptr, N, g, s, dt)" % (
+            struct, W, plan.min_blocks["fd_grad"], lam)
+        if fam == "tps+pipe":
+            L.append("    if (use_pipe(N)) return %s;" % pipe_call)
+            L.append("    return %s;" % tps_call)
+        elif fam == "pipe":
+            L.append("    return %s;" % pipe_call)
+        elif fam == "tps":
+            L.append("    return %s;" % tps_call)
+        else:
+            L.append("    return cudaErrorNotSupported;")
+        L.append("}")
+
+    kinds = "\n".join('    if (!strcmp(alg, "%s")) return "%s";' % (a, k)
+                      for a, k in list(plan.kind.items()) + list(plan.consumers.items()))
     fl = "\n".join('    if (!strcmp(alg, "%s")) return %d;' % (
         a, stats[needed[a][0]]["flops"] if "tps" in plan.kind[a] else plan.pipe[needed[a][0]].flops)
         for a in plan.kind if "tps" in plan.kind[a] or "pipe" in plan.kind[a])
+    fl += "\n" + "\n".join('    if (!strcmp(alg, "%s")) return %d;' % (
+        c, stats[c]["flops"] if "tps" in fam else plan.pipe[c].flops)
+        for c, fam in plan.consumers.items() if fam != "none")
     out.append("#include <cstring>\n#include <cstdlib>\n")
     out.append(_LAUNCHERS % {"launchers": "\n".join(L), "kinds": kinds, "flops": fl})
     out.append('#include "grid_abi.cuh"\n')

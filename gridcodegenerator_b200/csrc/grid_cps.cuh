@@ -37,10 +37,12 @@ cudaError_t cps_launch(float *d_out, const float *d_in0, int stride0, const floa
     if (num_states <= 0) return cudaSuccess;
     constexpr int SPW = 32 / G;
     long long groups = ((long long)num_states + SPW - 1) / SPW;
-    static int cap = 0;
+    static int caps[kMaxDevices];
+    int dev = 0;
+    if (cudaError_t e = current_device(dev)) return e;
+    int &cap = caps[dev];
     if (cap == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
+        int sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cps_kernel<C, G>, 32, 0);
         cap = sms * (per_sm > 0 ? per_sm : 1);

@@ -132,7 +132,7 @@ template <class P, int STAGE>
 __global__ void __launch_bounds__(32 * P::WARPS, STAGE == 0 ? P::MINB0 : P::MINB1)
 pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0, const float *__restrict__ d_in1,
             float *__restrict__ scratch, unsigned int *__restrict__ ticket, int num_states, int ntiles, int nblk,
-            float gravity) {
+            float gravity, float dt) {
     using S = PipeShape<P>;
     constexpr int NTASKS = STAGE == 0 ? P::NTASKS0 : P::NTASKS1;
     extern __shared__ float smem_all[];
@@ -182,7 +182,7 @@ pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stri
         const int src = min(lane, cnt - 1);
         float *sc = scratch + (long long)tile * (P::SCRATCH_WORDS * 32) + lane;
         P::template run<STAGE>(task, smem + src * S::IN_PAD, sc, sc, s_warp + lane * P::STAGE_PAD,
-                               d_out + first * P::OUT, owner ? cnt : 0, lane, s_warp, gravity);
+                               d_out + first * P::OUT, owner ? cnt : 0, lane, s_warp, gravity, dt);
         __syncwarp();
     }
 }
@@ -192,7 +192,7 @@ pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stri
 // (Atlas FD gradient at 8 192 states: 3 x 32 items of 8 tiles would occupy 96 of 148 SMs).
 template <class P, int STAGE>
 cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, const float *d_in1, float *scratch,
-                              unsigned int *ticket, int num_states, float gravity, cudaStream_t stream) {
+                              unsigned int *ticket, int num_states, float gravity, cudaStream_t stream, float dt) {
     using S = PipeShape<P>;
     constexpr int ntasks = STAGE == 0 ? P::NTASKS0 : P::NTASKS1;
     if (ntasks == 0) return cudaSuccess;
@@ -201,10 +201,14 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
     // candidate CTA sizes: 1, 2, 4, 8 warps and the size the kernel was compiled for
     constexpr int NOPT = 5;
     static const int opt_w[NOPT] = {1, 2, 4, 8, P::WARPS};
-    static int sms = 0, per_sm[NOPT] = {0, 0, 0, 0, 0};     // resident CTAs per SM per option (benign race)
+    struct DevCfg { int sms, per_sm[NOPT]; };               // resident CTAs per SM per option
+    static DevCfg cfgs[kMaxDevices];                        // per device (benign race: idempotent)
+    int dev = 0;
+    if (cudaError_t e = current_device(dev)) return e;
+    int &sms = cfgs[dev].sms;
+    int *per_sm = cfgs[dev].per_sm;
     if (sms == 0) {
-        int dev = 0, n = 0, smem_max = 0;
-        cudaGetDevice(&dev);
+        int n = 0, smem_max = 0;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         size_t want = warp_smem * P::WARPS;
@@ -237,7 +241,8 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
     const long long cap = (long long)sms * per_sm[wi];
     const int blocks = (int)(items < cap ? items : cap);
     kern<<<blocks, 32 * w, warp_smem * w, stream>>>(d_out, d_in0, stride0, d_in1, scratch,
-                                                    items > cap ? ticket : nullptr, num_states, ntiles, nblk, gravity);
+                                                    items > cap ? ticket : nullptr, num_states, ntiles, nblk, gravity,
+                                                    dt);
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -258,10 +263,11 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
 // callers on different streams); keeping the pool's memory between calls makes the allocation a
 // free-list hit after the first launch.
 static void keep_pool_memory() {
-    static bool done = false;
-    if (done) return;
+    static bool dones[kMaxDevices];
     int dev = 0;
-    cudaGetDevice(&dev);
+    if (current_device(dev) != cudaSuccess) return;
+    bool &done = dones[dev];
+    if (done) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         unsigned long long keep = ~0ull;
@@ -278,7 +284,7 @@ template <class P>
 __global__ void __launch_bounds__(32 * P::WARPS, 1)
 pipe_fused_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0,
                   const float *__restrict__ d_in1, float *__restrict__ scratch, int *__restrict__ flags, int num_states,
-                  int ntiles, int nblk, float gravity, const PipePart part) {
+                  int ntiles, int nblk, float gravity, float dt, const PipePart part) {
     using S = PipeShape<P>;
     extern __shared__ float smem_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -314,10 +320,10 @@ pipe_fused_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, in
         float *sc = scratch + (long long)tile * (P::SCRATCH_WORDS * 32) + lane;
         if (stage0)
             P::template run<0>(k, smem + src * S::IN_PAD, sc, sc, s_warp + lane * P::STAGE_PAD, d_out + first * P::OUT,
-                               owner ? cnt : 0, lane, s_warp, gravity);
+                               owner ? cnt : 0, lane, s_warp, gravity, dt);
         else
             P::template run<1>(k - P::NTASKS0, smem, sc, sc, s_warp + lane * P::STAGE_PAD, d_out + first * P::OUT,
-                               owner ? cnt : 0, lane, s_warp, gravity);
+                               owner ? cnt : 0, lane, s_warp, gravity, dt);
         if (stage0 && P::SCRATCH_WORDS > 0) {
             __threadfence();
             __syncwarp();
@@ -355,17 +361,19 @@ static int pipe_partition(int G, int nblk, PipePart &part) {
 
 template <class P>
 cudaError_t pipe_fused_launch(float *d_out, const float *d_in0, int stride0, const float *d_in1, int num_states,
-                              float gravity, cudaStream_t stream, bool &handled) {
+                              float gravity, cudaStream_t stream, bool &handled, float dt) {
     using S = PipeShape<P>;
     handled = false;
     auto kern = pipe_fused_kernel<P>;
     constexpr size_t smem_bytes = sizeof(float) * S::smem_words(0) * P::WARPS;
-    static int cap = 0;
+    static int caps[kMaxDevices];
+    int dev = 0;
+    if (cudaError_t e = current_device(dev)) return e;
+    int &cap = caps[dev];
     if (cap == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
+        int sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * P::WARPS, smem_bytes);
         if (e != cudaSuccess) return e;
@@ -389,7 +397,7 @@ cudaError_t pipe_fused_launch(float *d_out, const float *d_in0, int stride0, con
     if (e == cudaSuccess) {
         kern<<<blocks, 32 * P::WARPS, smem_bytes, stream>>>(d_out, d_in0, stride0, d_in1, (float *)buf,
                                                             (int *)(buf + sc_bytes), num_states, ntiles, nblk, gravity,
-                                                            part);
+                                                            dt, part);
         g_kernel_launches.fetch_add(1);
         e = cudaGetLastError();
     }
@@ -404,7 +412,7 @@ cudaError_t pipe_fused_launch(float *d_out, const float *d_in0, int stride0, con
 // Entry point: both stages on `stream` (or the experimental fused kernel, see below).
 template <class P>
 cudaError_t pipe_launch(float *d_out, const float *d_in0, int stride0, const float *d_in1, int num_states,
-                        float gravity, cudaStream_t stream) {
+                        float gravity, cudaStream_t stream, float dt = 0.f) {
     if (num_states <= 0) return cudaSuccess;
     g_calls.fetch_add(1);
     float *scratch = nullptr;
@@ -413,11 +421,10 @@ cudaError_t pipe_launch(float *d_out, const float *d_in0, int stride0, const flo
     // it) but measured SLOWER than the staged kernels on every robot (Atlas FD gradient 975 vs 760 us,
     // HyQ 56 vs 43 us, profiles/r1_pipe_fused_vs_staged.md): SMs of one GPC running different programs
     // lose the sharing of the instruction stream in the GPC-level cache.
-    const char *f = getenv("GRID_PIPE_MODE");
-    const bool fused = f && !strcmp(f, "fused");
+    const bool fused = options().pipe_fused != 0;
     if (fused && P::NT > 1) {
         bool handled = false;
-        e = pipe_fused_launch<P>(d_out, d_in0, stride0, d_in1, num_states, gravity, stream, handled);
+        e = pipe_fused_launch<P>(d_out, d_in0, stride0, d_in1, num_states, gravity, stream, handled, dt);
         if (handled || e != cudaSuccess) return e;
     }
     // Two-stage variants can run in chunks of P::CHUNK_STATES states (a multiple of 32; GRID_PIPE_CHUNK
@@ -426,21 +433,16 @@ cudaError_t pipe_launch(float *d_out, const float *d_in0, int stride0, const flo
     // 769 us unchunked, 789 / 979 / 1083 us with 32 k / 16 k / 8 k chunks) - fewer tiles per task per SM
     // means less re-execution of a program while it is in the instruction caches.
     int chunk = num_states;
-    static int chunk_cfg = -1;
-    if (chunk_cfg < 0) {
-        const char *c = getenv("GRID_PIPE_CHUNK");
-        chunk_cfg = c ? atoi(c) / 32 * 32 : P::CHUNK_STATES;
-    }
+    const int chunk_cfg = options().pipe_chunk >= 0 ? options().pipe_chunk : P::CHUNK_STATES;
     if (P::SCRATCH_WORDS > 0 && chunk_cfg > 0 && chunk_cfg < num_states) chunk = chunk_cfg;
     const int nchunks = (num_states + chunk - 1) / chunk;
     // one allocation: [ticket counters: 2 per chunk, padded to 256 B | scratch words of one chunk];
     // small batches need no tickets, single-stage variants no scratch
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    static int sms_of[kMaxDevices];
+    int dev = 0;
+    if (cudaError_t e0 = current_device(dev)) return e0;
+    int &sms = sms_of[dev];
+    if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     constexpr int max_tasks = P::NTASKS0 > P::NTASKS1 ? P::NTASKS0 : P::NTASKS1;
     const long long max_items = (long long)max_tasks * (((chunk + 31) / 32 + P::WARPS - 1) / P::WARPS);
     // (the counters cost a memset node: ~1.5 us, visible on 10 us launches such as HyQ Minv at 16 384
@@ -468,9 +470,10 @@ cudaError_t pipe_launch(float *d_out, const float *d_in0, int stride0, const flo
         float *o = d_out + (long long)first * P::OUT;
         const float *i0 = d_in0 + (long long)first * stride0;
         const float *i1 = d_in1 ? d_in1 + (long long)first * P::IN1 : nullptr;
-        e = pipe_stage_launch<P, 0>(o, i0, stride0, i1, sc, tickets ? tickets + 2 * c : nullptr, n, gravity, stream);
+        e = pipe_stage_launch<P, 0>(o, i0, stride0, i1, sc, tickets ? tickets + 2 * c : nullptr, n, gravity, stream, dt);
         if (e == cudaSuccess)
-            e = pipe_stage_launch<P, 1>(o, i0, stride0, i1, sc, tickets ? tickets + 2 * c + 1 : nullptr, n, gravity, stream);
+            e = pipe_stage_launch<P, 1>(o, i0, stride0, i1, sc, tickets ? tickets + 2 * c + 1 : nullptr, n, gravity, stream,
+                                        dt);
     }
     if (scratch) {
         cudaError_t e2 = cudaFreeAsync(scratch, stream);

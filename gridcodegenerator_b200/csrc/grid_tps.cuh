@@ -9,8 +9,52 @@
 // is state-major.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
+#include <cstring>
 
 namespace GRID_NS {
+
+// ---- process-wide options --------------------------------------------------------------------
+// Read from the environment ONCE (first use), changed afterwards only through grid_set_option()
+// (include/grid_b200.h): the launch path never calls getenv.
+enum ForceKernel { kAuto = 0, kTps = 1, kWps = 2, kCps = 3, kPipe = 4 };
+struct Options {
+    int force_kernel;       // ForceKernel
+    int pipe_fused;         // 1 = experimental single-launch variant of the phase-split kernels
+    int pipe_chunk;         // states per chunk of a two-stage launch; -1 = the compiled default
+};
+inline int parse_force(const char *f) {
+    if (!f || !*f) return kAuto;
+    if (!strcmp(f, "tps")) return kTps;
+    if (!strcmp(f, "wps")) return kWps;
+    if (!strcmp(f, "cps")) return kCps;
+    if (!strcmp(f, "pipe")) return kPipe;
+    return -1;
+}
+inline Options &options() {
+    static Options o = [] {
+        Options x;
+        const int f = parse_force(getenv("GRID_FORCE_KERNEL"));
+        x.force_kernel = f < 0 ? kAuto : f;
+        const char *m = getenv("GRID_PIPE_MODE");
+        x.pipe_fused = (m && !strcmp(m, "fused")) ? 1 : 0;
+        const char *c = getenv("GRID_PIPE_CHUNK");
+        x.pipe_chunk = c ? atoi(c) / 32 * 32 : -1;
+        return x;
+    }();
+    return o;
+}
+
+// ---- per-device launch state -----------------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize), the SM count and the occupancy caps belong to a
+// device, and one process may drive several (a torch user calling cuda:0 then cuda:1): every
+// launcher keeps its cached state in an array indexed by the CURRENT device.
+constexpr int kMaxDevices = 64;
+inline cudaError_t current_device(int &dev) {
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    return (dev < 0 || dev >= kMaxDevices) ? cudaErrorInvalidDevice : cudaSuccess;
+}
 
 constexpr int odd_pad(int words) { return words | 1; }   // odd stride => conflict-free lane access
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
@@ -70,7 +114,7 @@ __device__ __forceinline__ void warp_copy_s2g(float *__restrict__ dst, const flo
 template <class A>
 __device__ __forceinline__ void tps_body(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0,
                                          const float *__restrict__ d_in1, const float *__restrict__ d_in2,
-                                         int num_states, float gravity) {
+                                         int num_states, float gravity, float dt) {
     using S = TpsShape<A>;
     extern __shared__ float smem[];
     unsigned smem_bytes;
@@ -100,7 +144,7 @@ __device__ __forceinline__ void tps_body(float *__restrict__ d_out, const float 
         __syncwarp();
         // lanes past the end of a ragged tile recompute the last valid state (results dropped)
         const int src = max(0, min(lane, cnt - 1));
-        if (worker) A::eval(sw + src * S::IN_PAD, sw + lane * S::OUT_PAD, gravity);
+        if (worker) A::eval(sw + src * S::IN_PAD, sw + lane * S::OUT_PAD, gravity, dt);
         __syncwarp();
         float *dst = d_out + first * A::OUT;
         if (S::OUT_LINEAR && aligned16(dst)) {
@@ -118,8 +162,8 @@ __device__ __forceinline__ void tps_body(float *__restrict__ d_out, const float 
 template <class A, int WARPS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(32 * WARPS, MIN_BLOCKS)
 tps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0,
-           const float *__restrict__ d_in1, const float *__restrict__ d_in2, int num_states, float gravity) {
-    tps_body<A>(d_out, d_in0, stride0, d_in1, d_in2, num_states, gravity);
+           const float *__restrict__ d_in1, const float *__restrict__ d_in2, int num_states, float gravity, float dt) {
+    tps_body<A>(d_out, d_in0, stride0, d_in1, d_in2, num_states, gravity, dt);
 }
 
 // ---- variant 2: per-column output flush + parked per-state data ------------------------------
@@ -175,13 +219,15 @@ cudaError_t tps2_launch(float *d_out, const float *d_in0, int stride0, const flo
     if (num_states <= 0) return cudaSuccess;
     auto kern = tps2_kernel<A, WARPS, MIN_BLOCKS>;
     constexpr size_t smem_bytes = sizeof(float) * S::WARP_WORDS * WARPS;
-    static int cap = 0;
+    static int caps[kMaxDevices];               // resident CTAs per device (benign race: idempotent)
+    int dev = 0;
+    if (cudaError_t e = current_device(dev)) return e;
+    int &cap = caps[dev];
     if (cap == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
+        int sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * WARPS, smem_bytes);
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
@@ -196,29 +242,27 @@ cudaError_t tps2_launch(float *d_out, const float *d_in0, int stride0, const flo
 
 template <class A, int WARPS, int MIN_BLOCKS>
 cudaError_t tps_launch(float *d_out, const float *d_in0, int stride0, const float *d_in1, const float *d_in2,
-                       int num_states, float gravity, cudaStream_t stream) {
+                       int num_states, float gravity, cudaStream_t stream, float dt = 0.f) {
     using S = TpsShape<A>;
     if (num_states <= 0) return cudaSuccess;
     auto kern = tps_kernel<A, WARPS, MIN_BLOCKS>;
     constexpr size_t smem_bytes = sizeof(float) * S::WARP_WORDS * WARPS;
-    static bool configured = false;             // benign race: idempotent attribute set
-    if (!configured) {
+    static int caps[kMaxDevices];               // resident CTAs per device; beyond it, CTAs loop (benign race)
+    int dev = 0;
+    if (cudaError_t e = current_device(dev)) return e;
+    int &cap = caps[dev];
+    if (cap == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    const int ntiles = (num_states + 31) / 32;
-    int blocks = (ntiles + WARPS - 1) / WARPS;
-    static int cap = 0;                         // resident CTAs on this device; beyond it, CTAs loop
-    if (cap == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
+        int sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * WARPS, smem_bytes);
         cap = sms * (per_sm > 0 ? per_sm : 1);
     }
+    const int ntiles = (num_states + 31) / 32;
+    int blocks = (ntiles + WARPS - 1) / WARPS;
     if (blocks > cap) blocks = cap;
-    kern<<<blocks, 32 * WARPS, smem_bytes, stream>>>(d_out, d_in0, stride0, d_in1, d_in2, num_states, gravity);
+    kern<<<blocks, 32 * WARPS, smem_bytes, stream>>>(d_out, d_in0, stride0, d_in1, d_in2, num_states, gravity, dt);
     return cudaGetLastError();
 }
 

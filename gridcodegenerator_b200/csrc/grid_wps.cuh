@@ -634,12 +634,14 @@ cudaError_t wps_launch(float *d_out, const float *d_in, int stride, const float 
     if (num_states <= 0) return cudaSuccess;
     auto kern = wps_kernel<ALG, EXTRA>;
     constexpr size_t smem_bytes = sizeof(float) * L::total;
-    static int cap = 0;
+    static int caps[kMaxDevices];
+    int dev = 0;
+    if (cudaError_t e = current_device(dev)) return e;
+    int &cap = caps[dev];
     if (cap == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
+        int sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem_bytes);
         if (e != cudaSuccess) return e;

@@ -715,7 +715,7 @@ class GRiDCodeGenerator:
         body = ["    static_assert(std::is_same<T,float>::value, \"T must be float\");"]
         if single_call_timing:
             body.append("    for (int rep = 0; rep < NUM_TIMESTEPS; rep++)")
-        body.append("    %s::tps_body<%s::gen::%s>(%s, %s, %s, %s, %s, %s, %s);" % (
+        body.append("    %s::tps_body<%s::gen::%s>(%s, %s, %s, %s, %s, %s, %s, 0.f);" % (
             ns, ns, struct, out, in_name, stride_name, in1, in2, count, g))
         self.gen_add_code_lines(body + ["}", ""])
 
@@ -1084,10 +1084,66 @@ class GRiDCodeGenerator:
         v, a, f = (vaf[k * 6 * n:(k + 1) * 6 * n].reshape(n, 6).T for k in range(3))
         return out["c"], v, a, f
 
+    # pass-level functions (reference _test.py:5-107, 117-202, 229-488): the forward/backward halves
+    # with the reference's argument lists and return tuples.  Halves that START an algorithm evaluate
+    # the traced program up to that point; halves that take intermediate arrays from the caller
+    # (test_rnea_bpass, test_minv_fpass) are a function of those arrays and run in numpy on them.
+    def test_rnea_fpass(self, q, qd, qdd=None, GRAVITY=-9.81):
+        n = self.robot.get_num_pos()
+        kw = dict(q=q, qd=qd, gravity=-GRAVITY)
+        if qdd is not None:
+            kw["qdd"] = qdd
+        vaf = self._eval(A.trace_rnea_fpass(self.robot, qdd is not None), **kw)["vaf"]
+        v, a, f = (vaf[k * 6 * n:(k + 1) * 6 * n].reshape(n, 6).T.copy() for k in range(3))
+        return v, a, f
+
+    def test_rnea_bpass(self, q, qd, f):
+        """c_i = S_i^T f_i after f_parent += X_i^T f_i, children before parents; updates f in place
+        like the reference (_test.py:78-107)."""
+        n = self.robot.get_num_pos()
+        c = np.zeros(n)
+        for i in range(n - 1, -1, -1):                     # ids are a DFS pre-order: child > parent
+            c[i] = f[int(np.argmax(self.robot.get_S_by_id(i))), i] + self.robot.get_damping_by_id(i) * qd[i]
+            par = self.robot.get_parent_id(i)
+            if par >= 0:
+                f[:, par] += self.robot.get_Xmat_Func_by_id(i)(q[i]).T @ f[:, i]
+        return c, f
+
+    def test_minv_bpass(self, q):
+        n = self.robot.get_num_pos()
+        out = self._eval(A.trace_minv_bpass(self.robot), q=q)
+        return (out["Minv"].reshape(n, n).copy(), out["F"].reshape(n, 6, n).copy(), out["U"].reshape(n, 6).copy(),
+                out["Dinv"].copy())
+
+    def test_minv_fpass(self, q, Minv, F, U, Dinv):
+        """Forward pass on caller-supplied (Minv, F, U, Dinv), joints in id order (_test.py:186-202)."""
+        n = self.robot.get_num_pos()
+        for i in range(n):
+            par = self.robot.get_parent_id(i)
+            k = int(np.argmax(self.robot.get_S_by_id(i)))
+            if par >= 0:
+                X = self.robot.get_Xmat_Func_by_id(i)(q[i])
+                XF = X @ F[par][:, i:]
+                Minv[i, i:] -= Dinv[i] * (U[i] @ XF)
+                F[i][:, i:] = XF
+            else:
+                F[i][:, i:] = 0.0
+            F[i][k, i:] += Minv[i, i:]
+        return Minv
+
     def test_minv(self, q, output_dense=True):
         n = self.robot.get_num_pos()
         M = self._eval(A.trace_minv(self.robot), q=q)["Minv"].reshape(n, n).T
         return self.test_densify_Minv(M) if output_dense else M
+
+    def test_rnea_grad_inner(self, q, qd, v, a, f, GRAVITY=-9.81):
+        """(dc_dq, dc_dqd, dv_dq, dv_dqd, da_dq, da_dqd, df_fp_dq, df_fp_dqd, df_dq, df_dqd) from the RNEA
+        results, 6 x n x n arrays indexed [row, column, joint] (_test.py:229-488)."""
+        n = self.robot.get_num_pos()
+        vaf = np.concatenate([np.asarray(x, dtype=np.float64).T.flatten() for x in (v, a, f)])
+        out = self._eval(A.trace_id_grad_inner(self.robot), q=q, qd=qd, vaf=vaf)
+        dc = out["dc_du"].reshape(2 * n, n).T
+        return (dc[:, :n].copy(), dc[:, n:].copy()) + tuple(out[k].reshape(6, n, n).copy() for k in A.GRAD_INNER_ARRAYS)
 
     def test_densify_Minv(self, Minv):
         return np.triu(Minv) + np.triu(Minv, 1).T

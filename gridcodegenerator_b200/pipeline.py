@@ -32,7 +32,7 @@ from __future__ import annotations
 from typing import Dict, List, Optional, Sequence, Tuple
 
 from .algorithms import (RneaResult, SymRobot, cross_motion_axis, minv, minv_get, rnea,
-                         rnea_grad_columns)
+                         rnea_grad_columns, vjp_column)
 from .ir import Program, V, dot
 from .robot import Robot
 
@@ -45,7 +45,13 @@ PIPE_VARIANTS = {
     "id_grad":     ("PipeIdGrad",     2, 0, lambda n: 2 * n * n),
     "id_grad_qdd": ("PipeIdGradQdd",  2, 1, lambda n: 2 * n * n),
     "fd_grad":     ("PipeFdGrad",     3, 0, lambda n: 2 * n * n),
+    # consumers fused after the FD gradient (algorithms.trace_fd_consumer documents the outputs);
+    # in1 = lam = [lam_q | lam_v]
+    "fd_vjp":      ("PipeFdVjp",      3, 2, lambda n: 5 * n),
+    "fd_lin":      ("PipeFdLin",      3, 0, lambda n: 2 * n + 3 * n * n),
 }
+FD_LIKE = ("fd_grad", "fd_vjp", "fd_lin")          # programs that start with RNEA(0), Minv, qdd
+GRAD_LIKE = ("id_grad",) + FD_LIKE                 # programs with du-columns (two-stage when large)
 
 
 def components(robot: Robot) -> List[List[int]]:
@@ -104,6 +110,35 @@ def _state_inputs(p: Program, n: int, ids: Sequence[int], block: int) -> List[V]
     return [p.inp("in:%d" % (block * n + g)) for g in ids]
 
 
+def _fd_prologue(p: Program, S: SymRobot, qd, u, g):
+    """RNEA(qdd = 0), Minv, qdd = Minv (u - c) of one component."""
+    nc = S.n
+    R0 = rnea(S, qd, None, g)
+    Mi = minv(S)
+    umc = [u[i] - R0.c[i] for i in range(nc)]
+    return Mi, [dot([minv_get(Mi, i, j) for j in range(nc)], umc) for i in range(nc)]
+
+
+def _xnext_outputs(p: Program, n: int, ids: Sequence[int], q, qd, qdd, dt):
+    """x+ = [q + dt qd ; qd + dt qdd] rows of one component: two runs of nc words."""
+    for l, gid in enumerate(ids):
+        p.output("out", gid, q[l] + dt * qd[l])
+        p.output("out", n + gid, qd[l] + dt * qdd[l])
+    return ((ids[0], n + ids[0]), len(ids))
+
+
+def _b2_outputs(p: Program, n: int, ids: Sequence[int], Mi, dt):
+    """Columns of B2 = dt Minv owned by one component (zeros outside it: Minv is block-diagonal)."""
+    nc, base, runs = len(ids), ids[0], []
+    for j in range(nc):
+        off = 2 * n + 2 * n * n + n * ids[j]
+        for ig in range(n):
+            l = ig - base
+            p.output("out", off + ig, dt * minv_get(Mi, l, j) if 0 <= l < nc else 0.0)
+        runs.append(((off,), n))
+    return runs
+
+
 def _trace_stage_a(robot: Robot, ids: Sequence[int], alg: str, use_qdd: bool):
     sub, n = subrobot(robot, ids), robot.n
     nc = sub.n
@@ -112,16 +147,28 @@ def _trace_stage_a(robot: Robot, ids: Sequence[int], alg: str, use_qdd: bool):
     g = p.inp("gravity")
     S = SymRobot(p, sub, q)
     Mi = None
-    if alg == "fd_grad":
+    runs: List[Tuple[Tuple[int, ...], int]] = []
+    ex = _Exports()
+    if alg in FD_LIKE:
         u = _state_inputs(p, n, ids, 2)
-        R0 = rnea(S, qd, None, g)
-        Mi = minv(S)
-        umc = [u[i] - R0.c[i] for i in range(nc)]
-        qdd = [dot([minv_get(Mi, i, j) for j in range(nc)], umc) for i in range(nc)]
+        Mi, qdd = _fd_prologue(p, S, qd, u, g)
     else:
         qdd = _state_inputs(p, n, ids, 2) if use_qdd else None      # in1 follows the 2n words of in0
+    if alg in ("fd_vjp", "fd_lin"):
+        dt = p.inp("dt")
+        runs.append(_xnext_outputs(p, n, ids, q, qd, qdd, dt))
+    if alg == "fd_vjp":
+        lam_q, lam_v = _state_inputs(p, n, ids, 3), _state_inputs(p, n, ids, 4)
+        w = [dot([minv_get(Mi, i, j) for j in range(nc)], lam_v) for i in range(nc)]
+        for l, gid in enumerate(ids):
+            p.output("out", 4 * n + gid, dt * w[l])
+            ex.add("w%d" % l, w[l])
+            ex.add("lq%d" % l, lam_q[l])
+            ex.add("lv%d" % l, lam_v[l])
+        runs.append(((4 * n + ids[0],), nc))
+    if alg == "fd_lin":
+        runs += _b2_outputs(p, n, ids, Mi, dt)
     R = rnea(S, qd, qdd, g)
-    ex = _Exports()
     for i in range(nc):
         k = sub.S_ind[i]
         if k < 3:
@@ -137,10 +184,10 @@ def _trace_stage_a(robot: Robot, ids: Sequence[int], alg: str, use_qdd: bool):
             ex.add("Iv%d_%d" % (i, r), R.Iv[i][r])
             ex.add("mXa%d_%d" % (i, r), mXa[r])
             ex.add("mf%d_%d" % (i, r), mf[r])
-    if Mi is not None:
+    if Mi is not None and alg != "fd_vjp":          # the costate product needs w = Minv lam_v, not Minv
         for (r, c), v in Mi.items():
             ex.add("M%d_%d" % (r, c), v)
-    return p, ex, sub
+    return p, ex, sub, runs
 
 
 class _ImportSource:
@@ -178,6 +225,40 @@ def _column_outputs(p: Program, n: int, ids: Sequence[int], j: int, cq, cqd, M):
     return ((n * jg, n * n + n * jg), n)
 
 
+def _lin_column_outputs(p: Program, n: int, ids: Sequence[int], j: int, cq, cqd, M, dt):
+    """Columns jg of A21 = dt dqdd/dq and A22 = I + dt dqdd/dqd (zeros / identity outside the component)."""
+    nc, base, jg = len(ids), ids[0], ids[j]
+    for s, col in ((0, cq), (1, cqd)):
+        rows = sorted(col)
+        scaled = [col[r] * dt for r in rows]
+        for ig in range(n):
+            l = ig - base
+            v = -dot([M(l, r) for r in rows], scaled) if 0 <= l < nc else p.const(0.0)
+            if s == 1 and ig == jg:
+                v = v + 1.0
+            p.output("out", 2 * n + s * n * n + n * jg + ig, v)
+    return ((2 * n + n * jg, 2 * n + n * n + n * jg), n)
+
+
+def _consume_columns(p: Program, n: int, ids: Sequence[int], alg: str, columns, M, dt, w=None, lam_q=None, lam_v=None):
+    """Turns the dc_du column pairs of `columns` into the output runs of `alg`."""
+    runs, done = [], []
+    for j, cq, cqd in columns:
+        if alg == "fd_vjp":
+            aq, av = vjp_column(p, cq, cqd, w, lam_q[j], lam_v[j], dt)
+            p.output("out", 2 * n + ids[j], aq)
+            p.output("out", 3 * n + ids[j], av)
+            done.append(j)
+        elif alg == "fd_lin":
+            runs.append(_lin_column_outputs(p, n, ids, j, cq, cqd, M, dt))
+        else:
+            runs.append(_column_outputs(p, n, ids, j, cq, cqd, M))
+    if done:                                         # a group holds contiguous joints: one run pair
+        assert done == list(range(done[0], done[0] + len(done)))
+        runs.append(((2 * n + ids[done[0]], 3 * n + ids[done[0]]), len(done)))
+    return runs
+
+
 def _trace_stage_b(robot: Robot, ids: Sequence[int], sub: Robot, joints: Sequence[int], alg: str, ex: _Exports):
     n, nc = robot.n, sub.n
     p = Program()
@@ -188,10 +269,14 @@ def _trace_stage_b(robot: Robot, ids: Sequence[int], sub: Robot, joints: Sequenc
     q = [None if rev[i] else imp("q%d" % i) for i in range(nc)]
     S = SymRobot(p, sub, q, trig=(sin, cos))
     qd = [imp("qd%d" % i) for i in range(nc)]
-    M = (lambda r, c: imp("M%d_%d" % (min(r, c), max(r, c)))) if alg == "fd_grad" else None
-    runs = []
-    for j, cq, cqd in rnea_grad_columns(S, qd, None, src=_ImportSource(imp), joints=joints):
-        runs.append(_column_outputs(p, n, ids, j, cq, cqd, M))
+    M = (lambda r, c: imp("M%d_%d" % (min(r, c), max(r, c)))) if alg in ("fd_grad", "fd_lin") else None
+    dt = p.inp("dt") if alg in ("fd_vjp", "fd_lin") else None
+    kw = {}
+    if alg == "fd_vjp":
+        kw = dict(w=[imp("w%d" % i) for i in range(nc)], lam_q={j: imp("lq%d" % j) for j in joints},
+                  lam_v={j: imp("lv%d" % j) for j in joints})
+    runs = _consume_columns(p, n, ids, alg, rnea_grad_columns(S, qd, None, src=_ImportSource(imp), joints=joints),
+                            M, dt, **kw)
     return p, runs
 
 
@@ -228,19 +313,27 @@ def _trace_full(robot: Robot, ids: Sequence[int], alg: str, use_qdd: bool):
         for i in range(nc):
             p.output("out", ids[i], dot([minv_get(Mi, i, j) for j in range(nc)], umc))
         return p, [((base,), nc)]
-    M = None
-    if alg == "fd_grad":
+    M, dt, kw = None, None, {}
+    if alg in FD_LIKE:
         u = _state_inputs(p, n, ids, 2)
-        R0 = rnea(S, qd, None, g)
-        Mi = minv(S)
-        umc = [u[i] - R0.c[i] for i in range(nc)]
-        qdd = [dot([minv_get(Mi, i, j) for j in range(nc)], umc) for i in range(nc)]
+        Mi, qdd = _fd_prologue(p, S, qd, u, g)
         M = lambda r, c: minv_get(Mi, r, c)
     else:
         qdd = _state_inputs(p, n, ids, 2) if use_qdd else None
+    if alg in ("fd_vjp", "fd_lin"):
+        dt = p.inp("dt")
+        runs.append(_xnext_outputs(p, n, ids, q, qd, qdd, dt))
+    if alg == "fd_vjp":
+        lam_q, lam_v = _state_inputs(p, n, ids, 3), _state_inputs(p, n, ids, 4)
+        w = [dot([minv_get(Mi, i, j) for j in range(nc)], lam_v) for i in range(nc)]
+        for l, gid in enumerate(ids):
+            p.output("out", 4 * n + gid, dt * w[l])
+        runs.append(((4 * n + ids[0],), nc))
+        kw = dict(w=w, lam_q=lam_q, lam_v=lam_v)
+    if alg == "fd_lin":
+        runs += _b2_outputs(p, n, ids, Mi, dt)
     R = rnea(S, qd, qdd, g)
-    for j, cq, cqd in rnea_grad_columns(S, qd, R):
-        runs.append(_column_outputs(p, n, ids, j, cq, cqd, M))
+    runs += _consume_columns(p, n, ids, alg, rnea_grad_columns(S, qd, R), M, dt, **kw)
     return p, runs
 
 
@@ -263,13 +356,13 @@ class PipeVariant:
         for ci, ids in enumerate(components(robot)):
             pf, runs = _trace_full(robot, ids, alg, use_qdd)
             full = PipeTask("c%d_full" % ci, 0, pf, runs, ci)
-            if alg not in ("id_grad", "fd_grad") or full.flops <= single_stage_max_flops:
+            if alg not in GRAD_LIKE or full.flops <= single_stage_max_flops:
                 if full.flops > stage_a_max_flops:
                     self.feasible = False
                 self.tasks.append(full)
                 continue
             # two stages: A = state program, B = groups of du-columns
-            pa, ex, sub = _trace_stage_a(robot, ids, alg, use_qdd)
+            pa, ex, sub, runs_a = _trace_stage_a(robot, ids, alg, use_qdd)
             nc = sub.n
             # cost of every single column pair, then greedy packing of contiguous joints
             cost = []
@@ -299,7 +392,7 @@ class PipeVariant:
             sc_base += len(word_of)
             for node, w in word_of.items():
                 pa.output("sc", w, V(pa, i=node))
-            ta = PipeTask("c%d_A" % ci, 0, pa, [], ci)
+            ta = PipeTask("c%d_A" % ci, 0, pa, runs_a, ci)
             if ta.flops > stage_a_max_flops:
                 self.feasible = False
             self.tasks.append(ta)
@@ -314,7 +407,7 @@ class PipeVariant:
         self.stage_tasks = [sorted([t for t in self.tasks if t.stage == s], key=lambda t: -t.flops) for s in (0, 1)]
         self.flops = sum(t.flops for t in self.tasks)
 
-    def evaluate(self, in_rows, gravity: float = 9.81, dtype=None):
+    def evaluate(self, in_rows, gravity: float = 9.81, dtype=None, dt: float = 0.0):
         """Interprets the task programs with numpy in kernel order (stage 0, then stage 1) - the
         host-side check of the decomposition (tests/test_pipeline.py); never a product path.
         in_rows: (N, IN0 + IN1) array; returns (N, OUT) with NaN in words no task wrote."""
@@ -330,6 +423,8 @@ class PipeVariant:
                 for name in t.program.inputs:
                     if name == "gravity":
                         inputs[name] = dtype(gravity)
+                    elif name == "dt":
+                        inputs[name] = dtype(dt)
                     elif name.startswith("in:"):
                         inputs[name] = rows[:, int(name[3:])]
                     else:
@@ -375,8 +470,8 @@ def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead
     load_pos: Dict[int, int] = {}
     for o, fu in first_use.items():
         name = p.nodes[o][1]
-        if name == "gravity":
-            stmt, lead = "const float t%d = gravity;" % o, 0
+        if name in ("gravity", "dt"):
+            stmt, lead = "const float t%d = %s;" % (o, name), 0
         elif name.startswith("in:"):
             stmt, lead = "const float t%d = s_in[%d];" % (o, int(name[3:])), tile_lead
         else:
@@ -431,7 +526,7 @@ def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead
     body: List[str] = ["    // %s: %d mul + %d add per state" % (t.name, t.counts["mul"], t.counts["add"]),
                        "    static __device__ __noinline__ void %s(const float *s_in, const float *__restrict__ sc_in,"
                        " float *__restrict__ sc_out, float *s_stage, float *__restrict__ g_tile, const int cnt,"
-                       " const int lane, const float *s_warp, const float gravity) {" % fname,
+                       " const int lane, const float *s_warp, const float gravity, const float dt) {" % fname,
                        # the call boundary hides the address space: without this the staging accesses
                        # compile to generic LD/ST instead of LDS/STS
                        indent + "__builtin_assume(__isShared(s_in)); __builtin_assume(__isShared(s_stage));"
@@ -509,14 +604,15 @@ def emit_pipe_struct(pv: PipeVariant, min_blocks: Tuple[int, int] = (1, 1), warp
                              scratch_lead=scratch_lead)
     txt.append("    template <int STAGE> static __device__ __forceinline__ void run(const int task, const float *s_in,"
                " const float *__restrict__ sc_in, float *__restrict__ sc_out, float *s_stage,"
-               " float *__restrict__ g_tile, const int cnt, const int lane, const float *s_warp, const float gravity) {")
+               " float *__restrict__ g_tile, const int cnt, const int lane, const float *s_warp, const float gravity,"
+               " const float dt) {")
     for s in (0, 1):
         if not pv.stage_tasks[s]:
             continue
         txt.append("        if (STAGE == %d) {" % s)
         txt.append("            switch (task) {")
         for ti in range(len(pv.stage_tasks[s])):
-            txt.append("            case %d: s%d_t%d(s_in, sc_in, sc_out, s_stage, g_tile, cnt, lane, s_warp, gravity); break;"
+            txt.append("            case %d: s%d_t%d(s_in, sc_in, sc_out, s_stage, g_tile, cnt, lane, s_warp, gravity, dt); break;"
                        % (ti, s, ti))
         txt.append("            default: break;")
         txt.append("            }")

@@ -19,7 +19,11 @@
  *   - `grid_*` entry points taking a grid_data* are the reference's mode-0 host functions:
  *     H2D from the handle's pinned h_* inputs, kernel, D2H into the pinned h_* outputs,
  *     then synchronise;
- *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails;
+ *   - several devices in one process are supported: every launcher keeps its cached state (shared-
+ *     memory opt-in, occupancy caps) per device and uses the CURRENT device (cudaSetDevice); a
+ *     grid_data handle belongs to the device that was current when it was created and its host
+ *     functions fail with a message when called under another device.
  */
 #ifndef GRID_B200_H
 #define GRID_B200_H
@@ -28,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GRID_B200_ABI_VERSION 1
+#define GRID_B200_ABI_VERSION 2
 
 /* ---- identity --------------------------------------------------------------------- */
 int grid_abi_version(void);
@@ -74,6 +78,27 @@ int grid_inverse_dynamics_gradient_device(float *d_dc_du, const float *d_q_qd, i
 int grid_forward_dynamics_gradient_device(float *d_df_du, const float *d_q_qd_u, int stride, const float *d_qdd,
                                           const float *d_Minv, int num_timesteps, float gravity, void *stream);
 
+/* ---- consumers fused after the FD gradient (beyond the reference) -------------
+ * The reference's forward_dynamics_gradient stops at writing df_du (2n^2 floats per state) to
+ * global memory and copying it to the host (algorithms/_forward_dynamics_gradient.py:159-161,
+ * 235-238).  These two entry points trace the consumer INTO the gradient kernel, so df_du never
+ * leaves the registers.  Explicit Euler with step dt on x = [q; qd]:
+ *     x+ = x + dt [qd; qdd(q,qd,u)],   A = dx+/dx = [[I, dt I], [dt dqdd/dq, I + dt dqdd/dqd]],
+ *     B = dx+/du = [[0], [dt Minv]].
+ *
+ * grid_forward_dynamics_gradient_vjp_device: costate step of a shooting / DDP backward pass.
+ *   d_lambda: [lam_q (n) | lam_v (n)] per state;  d_out: 5n per state =
+ *   [x+ (2n) | A^T lam (2n) | B^T lam (n)].
+ * grid_forward_dynamics_linearize_device: the non-constant blocks of A and B.
+ *   d_out: 2n + 3n^2 per state = [x+ (2n) | A21 = dt dqdd/dq | A22 = I + dt dqdd/dqd | B2 = dt Minv],
+ *   the three n x n blocks column-major, B2 full symmetric.
+ * Available when the robot's FD gradient is served by the thread-per-state or phase-split kernels
+ * (grid_kernel_kind("fd_vjp") / ("fd_lin") != "none"); otherwise they fail with a message. */
+int grid_forward_dynamics_gradient_vjp_device(float *d_out, const float *d_q_qd_u, int stride, const float *d_lambda,
+                                              int num_timesteps, float dt, float gravity, void *stream);
+int grid_forward_dynamics_linearize_device(float *d_out, const float *d_q_qd_u, int stride, int num_timesteps, float dt,
+                                           float gravity, void *stream);
+
 /* ---- gridData-style handle (reference init_gridData / init_grid / close_grid) ------- */
 typedef struct grid_data grid_data;
 
@@ -85,8 +110,9 @@ void grid_data_destroy(grid_data *hd);
 int grid_data_capacity(const grid_data *hd);
 
 /* field access; names are the reference's gridData members:
- * "h_q_qd_u","h_q_qd","h_q","h_c","h_Minv","h_qdd","h_dc_du","h_df_du" and the d_* twins.
- * Returns NULL for an unknown name. */
+ * "h_q_qd_u","h_q_qd","h_q","h_c","h_Minv","h_qdd","h_dc_du","h_df_du" and the d_* twins, plus the
+ * consumer buffers "h_lambda" (2n), "h_vjp" (5n), "h_lin" (2n + 3n^2) and their d_* twins, which are
+ * allocated on first access.  Returns NULL for an unknown name. */
 float *grid_data_ptr(grid_data *hd, const char *field);
 
 /* mode-0 host functions: copy h_* -> d_*, run, copy result d_* -> h_*, synchronise.
@@ -98,12 +124,33 @@ int grid_direct_minv(grid_data *hd, int num_timesteps, int compressed);
 int grid_forward_dynamics(grid_data *hd, int num_timesteps, float gravity);
 int grid_inverse_dynamics_gradient(grid_data *hd, int num_timesteps, float gravity, int use_qdd, int compressed);
 int grid_forward_dynamics_gradient(grid_data *hd, int num_timesteps, float gravity, int use_qdd_minv);
+/* host forms of the fused consumers: h_q_qd_u (+ h_lambda) in, h_vjp / h_lin out */
+int grid_forward_dynamics_gradient_vjp(grid_data *hd, int num_timesteps, float dt, float gravity);
+int grid_forward_dynamics_linearize(grid_data *hd, int num_timesteps, float dt, float gravity);
+
+/* ---- repeated fixed-shape calls: CUDA graph ------------------------------------------------
+ * grid_graph_create captures ONE launch of `alg` ("id","minv","fd","id_grad","fd_grad","fd_vjp",
+ * "fd_lin") on the given device buffers (d_in1 = qdd or lambda, d_in2 = Minv, NULL when unused);
+ * grid_graph_launch replays it on `stream`.  For phase-split kernels the graph holds the scratch
+ * allocation, the ticket memset and both kernels.  The buffers must stay valid while the graph lives. */
+typedef struct grid_graph grid_graph;
+grid_graph *grid_graph_create(const char *alg, float *d_out, const float *d_in, int stride, const float *d_in1,
+                              const float *d_in2, int num_timesteps, float dt, float gravity);
+int grid_graph_launch(grid_graph *g, void *stream);
+void grid_graph_destroy(grid_graph *g);
+
+/* ---- options ------------------------------------------------------------------------------
+ * The environment variables GRID_FORCE_KERNEL (tps|wps|cps|pipe), GRID_PIPE_MODE (staged|fused) and
+ * GRID_PIPE_CHUNK (states) are read ONCE, at the first launch; afterwards they change only through
+ * this call (value NULL or "" restores the default).  Nothing on the launch path calls getenv. */
+int grid_set_option(const char *key, const char *value);
 
 /* ---- measurement helpers (not part of the reference API) ------------------------------ */
 /* Runs an FFMA-only microbenchmark on the current device and returns the measured FP32
  * (non-tensor) throughput in TFLOP/s (the roofline denominator); <0 on error. */
 double grid_measure_fp32_tflops(int repeats);
-/* Times `reps` back-to-back launches of one algorithm ("id","minv","fd","id_grad","fd_grad", inputs
+/* Times `reps` back-to-back launches of one algorithm ("id","minv","fd","id_grad","fd_grad"; with the
+ * suffix "@graph" the launch is captured once into a CUDA graph and the timed launches replay it; inputs
  * as for the matching *_device call with d_qdd = d_Minv = NULL) with one CUDA event pair per launch,
  * recorded from C so that no interpreter time sits between the events; h_us receives the `reps`
  * per-launch durations in microseconds.  This is how the N = 128 latency is measured.  alg = "noop" times an

