@@ -514,6 +514,75 @@ __device__ void grad_column(float *s, int ct, bool valid) {
 
 // ALG: 0 = Minv, 1 = FD, 2 = ID gradient, 3 = FD gradient.
 // EXTRA: ALG 2 -> qdd given (USE_QDD_FLAG); ALG 3 -> qdd and Minv given (USE_QDD_MINV_FLAG).
+//
+// wps_compute: one state, everything in the shared-memory block `s` (struct L).  On entry the inputs
+// are in place - s[L::q..] (q | qd | u as far as the algorithm reads them), for EXTRA s[L::qdd..] and,
+// ALG 3, the full symmetric Minv in s[L::Minv..] - and s[L::Ic..] holds the link inertias.  On exit:
+//   ALG 0: s[L::Minv + row * N + col], upper triangle (row <= col) valid
+//   ALG 1: s[L::qdd + i]
+//   ALG 2: s[L::dc + col * N + row] = dc_du       ALG 3: the same block holds df_du
+// All NT threads of the CTA must call; ends with a barrier.
+template <int ALG, bool EXTRA>
+__device__ __forceinline__ void wps_compute(float *s, float gravity) {
+    const int tid = threadIdx.x;
+    constexpr bool need_minv = (ALG == 0) || (ALG == 1) || (ALG == 3 && !EXTRA);
+    constexpr bool need_c0 = (ALG == 1) || (ALG == 3 && !EXTRA);
+    constexpr int RW = WT::RNEA_TID;                 // first thread of the RNEA warp
+    for (int i = tid; i < N; i += NT) update_X(s, i);
+    if (need_minv) {
+        for (int e = tid; e < 36 * N; e += NT) s[L::IA + e] = s[L::Ic + e];
+        for (int e = tid; e < N * N; e += NT) s[L::Minv + e] = 0.f;
+    }
+    __syncthreads();
+    // Minv passes on warps [0, RW/32), bias forces (RNEA with qdd = 0) concurrently on the RNEA warp
+    if (tid < RW) {
+        if (need_minv) minv_passes(s, tid);
+    } else {
+        if (need_c0) rnea_rows(s, tid - RW, false, gravity);
+    }
+    __syncthreads();
+    if (need_minv && ALG != 0) {                 // mirror the upper triangle: later reads are plain loads
+        for (int e = tid; e < N * N; e += NT) {
+            const int rr = e / N, cc = e - rr * N;
+            if (rr > cc) s[L::Minv + e] = s[L::Minv + cc * N + rr];
+        }
+        __syncthreads();
+    }
+    if (need_c0) {        // forward_dynamics_finish (algorithms/_forward_dynamics.py:21-49)
+        for (int r = tid; r < N; r += NT) {
+            float acc = 0.f;
+            for (int k = 0; k < N; k++) acc = fmaf(s[L::Minv + r * N + k], s[L::u + k] - s[L::c + k], acc);
+            s[L::qdd + r] = acc;
+        }
+        __syncthreads();
+    }
+    if (ALG >= 2) {
+        if (tid >= RW) rnea_rows(s, tid - RW, ALG == 3 ? true : EXTRA, gravity);
+        else
+            for (int e = tid; e < 2 * N * N; e += RW) s[L::dc + e] = 0.f;
+        __syncthreads();
+        if (tid < WT::COL_WARPS * 32)            // whole warps: grad_column votes with a full mask
+            grad_column(s, tid < 2 * N ? tid : 2 * N - 1, tid < 2 * N);
+        __syncthreads();
+        if (ALG == 3) {
+            // df_du[:, col] = -Minv dc_du[:, col]  (algorithms/_forward_dynamics_gradient.py:48-57)
+            // each lane owns one column: read it into registers, overwrite it in place
+            for (int col = tid; col < 2 * N; col += NT) {
+                float dcol[N];
+#pragma unroll
+                for (int k = 0; k < N; k++) dcol[k] = s[L::dc + col * N + k];
+                for (int r = 0; r < N; r++) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < N; k++) acc = fmaf(s[L::Minv + r * N + k], dcol[k], acc);
+                    s[L::dc + col * N + r] = -acc;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 template <int ALG, bool EXTRA>
 __device__ __forceinline__ void wps_body(float *__restrict__ d_out, const float *__restrict__ d_in, int stride,
                                          const float *__restrict__ d_qdd, const float *__restrict__ d_Minv,
@@ -521,10 +590,7 @@ __device__ __forceinline__ void wps_body(float *__restrict__ d_out, const float 
     extern __shared__ float4 smem4[];
     float *s = reinterpret_cast<float *>(smem4);
     const int tid = threadIdx.x;
-    constexpr bool need_minv = (ALG == 0) || (ALG == 1) || (ALG == 3 && !EXTRA);
-    constexpr bool need_c0 = (ALG == 1) || (ALG == 3 && !EXTRA);
     constexpr int n_in = (ALG == 0) ? N : ((ALG == 1 || (ALG == 3 && !EXTRA)) ? 3 * N : 2 * N);
-    constexpr int RW = WT::RNEA_TID;                 // first thread of the RNEA warp
 
     for (int e = tid; e < 36 * N; e += NT) s[L::Ic + e] = __ldg(wt_I_g + e);       // once per CTA
     for (long long st = blockIdx.x; st < num_states; st += gridDim.x) {
@@ -542,74 +608,65 @@ __device__ __forceinline__ void wps_body(float *__restrict__ d_out, const float 
                 }
         }
         __syncthreads();
-        for (int i = tid; i < N; i += NT) update_X(s, i);
-        if (need_minv) {
-            for (int e = tid; e < 36 * N; e += NT) s[L::IA + e] = s[L::Ic + e];
-            for (int e = tid; e < N * N; e += NT) s[L::Minv + e] = 0.f;
-        }
-        __syncthreads();
-        // Minv passes on warps [0, RW/32), bias forces (RNEA with qdd = 0) concurrently on the RNEA warp
-        if (tid < RW) {
-            if (need_minv) minv_passes(s, tid);
-        } else {
-            if (need_c0) rnea_rows(s, tid - RW, false, gravity);
-        }
-        __syncthreads();
-        if (need_minv && ALG != 0) {                 // mirror the upper triangle: later reads are plain loads
-            for (int e = tid; e < N * N; e += NT) {
-                const int rr = e / N, cc = e - rr * N;
-                if (rr > cc) s[L::Minv + e] = s[L::Minv + cc * N + rr];
-            }
-            __syncthreads();
-        }
+        wps_compute<ALG, EXTRA>(s, gravity);
         if (ALG == 0) {
             float *o = d_out + st * N * N;
             for (int e = tid; e < N * N; e += NT) {
                 const int cc = e / N, rr = e - cc * N;
                 o[e] = rr <= cc ? s[L::Minv + rr * N + cc] : 0.f;
             }
-        }
-        if (need_c0) {        // forward_dynamics_finish (algorithms/_forward_dynamics.py:21-49)
-            for (int r = tid; r < N; r += NT) {
-                float acc = 0.f;
-                for (int k = 0; k < N; k++) acc = fmaf(s[L::Minv + r * N + k], s[L::u + k] - s[L::c + k], acc);
-                s[L::qdd + r] = acc;
-            }
-            __syncthreads();
-            if (ALG == 1)
-                for (int r = tid; r < N; r += NT) d_out[st * N + r] = s[L::qdd + r];
-        }
-        if (ALG >= 2) {
-            if (tid >= RW) rnea_rows(s, tid - RW, ALG == 3 ? true : EXTRA, gravity);
-            else
-                for (int e = tid; e < 2 * N * N; e += RW) s[L::dc + e] = 0.f;
-            __syncthreads();
-            if (tid < WT::COL_WARPS * 32)            // whole warps: grad_column votes with a full mask
-                grad_column(s, tid < 2 * N ? tid : 2 * N - 1, tid < 2 * N);
-            __syncthreads();
+        } else if (ALG == 1) {
+            for (int r = tid; r < N; r += NT) d_out[st * N + r] = s[L::qdd + r];
+        } else {
             float *o = d_out + st * 2 * N * N;
-            if (ALG == 2) {
-                for (int e = tid; e < 2 * N * N; e += NT) o[e] = s[L::dc + e];
-            } else {
-                // df_du[:, col] = -Minv dc_du[:, col]  (algorithms/_forward_dynamics_gradient.py:48-57)
-                // each lane owns one column: read it into registers, overwrite it in place
-                for (int col = tid; col < 2 * N; col += NT) {
-                    float dcol[N];
-#pragma unroll
-                    for (int k = 0; k < N; k++) dcol[k] = s[L::dc + col * N + k];
-                    for (int r = 0; r < N; r++) {
-                        float acc = 0.f;
-#pragma unroll
-                        for (int k = 0; k < N; k++) acc = fmaf(s[L::Minv + r * N + k], dcol[k], acc);
-                        s[L::dc + col * N + r] = -acc;
-                    }
-                }
-                __syncthreads();
-                for (int e = tid; e < 2 * N * N; e += NT) o[e] = s[L::dc + e];
-            }
+            for (int e = tid; e < 2 * N * N; e += NT) o[e] = s[L::dc + e];
         }
         __syncthreads();
     }
+}
+
+// The reference's *_inner contract for robots whose single-thread program is too large (Atlas, 64-link
+// chain): inputs and output already in SHARED memory, scratch supplied by the caller
+// (GRiDCodeGenerator.py:249-276).  s_work = L::total floats of 16-byte aligned shared memory (what the
+// facade reports as gen_<alg>_inner_temp_mem_size()); blockDim.x must be NT.  s_x = u (ALG 1, 3 without
+// EXTRA) or qdd (EXTRA) or unused; s_Minv_in = column-major n x n, upper triangle read (ALG 3 with EXTRA).
+// Outputs in the reference's layouts: Minv column-major upper (strict lower 0), qdd[n], dc_du / df_du
+// column-major n x 2n.
+template <int ALG, bool EXTRA>
+__device__ __forceinline__ void wps_inner(float *s_out, const float *s_q, const float *s_qd, const float *s_x,
+                                          const float *s_Minv_in, float *s_work, float gravity) {
+    float *s = s_work;
+    const int tid = threadIdx.x;
+    __syncthreads();                                 // the caller's writes to its inputs are visible
+    for (int e = tid; e < 36 * N; e += NT) s[L::Ic + e] = __ldg(wt_I_g + e);
+    for (int e = tid; e < N; e += NT) {
+        s[L::q + e] = s_q[e];
+        if (ALG != 0) s[L::qd + e] = s_qd[e];
+        if (ALG == 1 || (ALG == 3 && !EXTRA)) s[L::u + e] = s_x[e];
+        if (EXTRA) s[L::qdd + e] = s_x[e];
+    }
+    if (ALG == 3 && EXTRA)
+        for (int e = tid; e < N * N; e += NT) {
+            const int cc = e / N, rr = e - cc * N;
+            if (rr <= cc) {
+                const float m = s_Minv_in[e];
+                s[L::Minv + rr * N + cc] = m;
+                s[L::Minv + cc * N + rr] = m;
+            }
+        }
+    __syncthreads();
+    wps_compute<ALG, EXTRA>(s, gravity);
+    if (ALG == 0) {
+        for (int e = tid; e < N * N; e += NT) {
+            const int cc = e / N, rr = e - cc * N;
+            s_out[e] = rr <= cc ? s[L::Minv + rr * N + cc] : 0.f;
+        }
+    } else if (ALG == 1) {
+        for (int r = tid; r < N; r += NT) s_out[r] = s[L::qdd + r];
+    } else {
+        for (int e = tid; e < 2 * N * N; e += NT) s_out[e] = s[L::dc + e];
+    }
+    __syncthreads();
 }
 
 }}  // namespace GRID_NS::wps

@@ -477,15 +477,69 @@ class GRiDCodeGenerator:
             "    gpuErrchk(cudaMemcpy(d_topology_helpers,h_topology_helpers,%d*sizeof(int),cudaMemcpyHostToDevice));" % len(tab),
             "    return d_topology_helpers;", "}", ""])
 
+    # ---- XI table: [X_0 .. X_{n-1} | (I_base) | I_0 .. I_{n-1}], 36 floats each, column-major
+    # (element (row, col) of matrix k at 36 k + 6 col + row: reference helpers/_topology_helpers.py:19-47).
+    # The traced programs never read it (their X_tree and inertias are immediates), but the reference's
+    # users do: a third-party kernel written against grid.cuh loads s_XImats with
+    # load_update_XImats_helpers() and applies X_i(q) / I_i itself.
+    def _ximats_entries(self):
+        """Per joint: {(row, col): (a, b, c)} with X[row, col](q) = a sin q + b cos q + c (revolute) or
+        a q + c (prismatic, b = 0), found numerically from the robot's own X(q) functions."""
+        out = []
+        for i in range(self.robot.get_num_pos()):
+            X = self.robot.get_Xmat_Func_by_id(i)
+            ent = {}
+            if self.robot.S_ind[i] < 3:
+                X0, X1, X2 = X(0.0), X(0.5 * np.pi), X(np.pi)
+                c = 0.5 * (X0 + X2)
+                a, b = X1 - c, 0.5 * (X0 - X2)
+            else:
+                X0, X1 = X(0.0), X(1.0)
+                c, a, b = X0, X1 - X0, np.zeros((6, 6))
+            for col in range(6):
+                for row in range(6):
+                    t = tuple(0.0 if abs(x) < 1e-14 else float("%.13g" % x) for x in (a[row, col], b[row, col], c[row, col]))
+                    ent[(row, col)] = t
+            out.append(ent)
+        return out
+
     def gen_init_XImats(self, include_base_inertia=False):
-        self.gen_add_code_line("// X_tree and inertia constants are immediates of the traced programs: no XI table")
+        n = self.robot.get_num_pos()
+        size = 72 * n + (36 if include_base_inertia else 0)
+        self.gen_add_func_doc("Initializes the Xmats and Imats in GPU memory",
+                              ["Memory order is X[0...N], %sI[0...N]; entries of X that depend on q are 0 until "
+                               "load_update_XImats_helpers fills them" % ("Ibase, " if include_base_inertia else "")],
+                              [], "A pointer to the XI memory in the GPU")
+        lines = ["template <typename T>", "__host__", "T* init_XImats() {",
+                 "    T *h_XImats = (T *)malloc(%d*sizeof(T));" % size]
+        for i, ent in enumerate(self._ximats_entries()):
+            lines.append("    // X[%d]" % i)
+            for col in range(6):
+                for row in range(6):
+                    a, b, c = ent[(row, col)]
+                    lines.append("    h_XImats[%d] = static_cast<T>(%s);" % (36 * i + 6 * col + row,
+                                                                          repr(c) if a == 0.0 and b == 0.0 else "0"))
+        Imats = self.robot.get_Imats_ordered_by_id()
+        if not include_base_inertia:
+            Imats = Imats[1:]
+        for k, I in enumerate(Imats):
+            lines.append("    // %s" % ("Base Inertia" if include_base_inertia and k == 0 else
+                                        "I[%d]" % (k - int(include_base_inertia))))
+            for col in range(6):
+                for row in range(6):
+                    lines.append("    h_XImats[%d] = static_cast<T>(%s);" % (36 * (n + k) + 6 * col + row,
+                                                                          repr(float(I[row, col]))))
+        lines += ["    T *d_XImats; gpuErrchk(cudaMalloc((void**)&d_XImats,%d*sizeof(T)));" % size,
+                  "    gpuErrchk(cudaMemcpy(d_XImats,h_XImats,%d*sizeof(T),cudaMemcpyHostToDevice));" % size,
+                  "    free(h_XImats);", "    return d_XImats;", "}", ""]
+        self.gen_add_code_lines(lines)
 
     def gen_init_robotModel(self):
-        self.gen_add_func_doc("Allocates the (empty) robotModel handle kept for API compatibility", [], [],
+        self.gen_add_func_doc("Initializes the robotModel helpers in GPU memory (XI table + topology table)", [], [],
                               "A pointer to the robotModel struct on the GPU")
         self.gen_add_code_lines([
             "template <typename T>", "__host__", "robotModel<T>* init_robotModel() {",
-            "    robotModel<T> h_robotModel; h_robotModel.d_XImats = nullptr;",
+            "    robotModel<T> h_robotModel; h_robotModel.d_XImats = init_XImats<T>();",
             "    h_robotModel.d_topology_helpers = init_topology_helpers<T>();",
             "    robotModel<T> *d_robotModel; gpuErrchk(cudaMalloc((void**)&d_robotModel,sizeof(robotModel<T>)));",
             "    gpuErrchk(cudaMemcpy(d_robotModel,&h_robotModel,sizeof(robotModel<T>),cudaMemcpyHostToDevice));",
@@ -506,20 +560,87 @@ class GRiDCodeGenerator:
             self.gen_add_code_lines([tmpl, "__host__", sig] + body + ["}", ""])
 
     def gen_load_update_XImats_helpers_temp_mem_size(self):
-        return 0
+        return 2 * self.robot.get_num_pos()          # sin | cos, as in the reference (_topology_helpers.py:56-58)
+
+    def _needs_topology_param(self):
+        n = self.robot.get_num_pos()
+        return not self.robot.is_serial_chain() or not self.robot.are_Ss_identical(list(range(n)))
 
     def gen_load_update_XImats_helpers_function_call(self, use_thread_group=False, updated_var_names=None):
-        self.gen_add_code_line("// X(q) is computed inside the traced programs")
+        v = dict(s_XImats_name="s_XImats", s_q_name="s_q", d_robotModel_name="d_robotModel", s_temp_name="s_temp",
+                 s_topology_helpers_name="s_topology_helpers")
+        v.update(updated_var_names or {})
+        args = [v["s_XImats_name"], v["s_q_name"]]
+        if self._needs_topology_param():
+            args.append(v["s_topology_helpers_name"])
+        self.gen_add_code_line("load_update_XImats_helpers<T>(%s);" % ", ".join(
+            args + [v["d_robotModel_name"], v["s_temp_name"]]))
 
     def gen_XImats_helpers_temp_shared_memory_code(self, temp_mem_size=None):
-        self.gen_add_code_line("T *s_XImats = nullptr; T *s_temp = nullptr;")
+        n = self.robot.get_num_pos()
+        words = self.gen_load_update_XImats_helpers_temp_mem_size() if temp_mem_size is None else temp_mem_size
+        if not self.use_dynamic_shared_mem_flag:
+            self.gen_add_code_line("__shared__ T s_XImats[%d];" % (72 * n))
+            if self._needs_topology_param():
+                self.gen_add_code_line("__shared__ int s_topology_helpers[%d];" % self.gen_topology_helpers_size())
+            self.gen_add_code_line("__shared__ T s_temp[%d];" % max(1, words))
+        else:
+            self.gen_add_code_line("extern __shared__ T s_XITemp[]; T *s_XImats = s_XITemp; ")
+            if self._needs_topology_param():
+                self.gen_add_code_line("int *s_topology_helpers = (int *)&s_XImats[%d];" % (72 * n))
+                self.gen_add_code_line("T *s_temp = (T *)&s_topology_helpers[%d];" % self.gen_topology_helpers_size())
+            else:
+                self.gen_add_code_line("T *s_temp = &s_XImats[%d];" % (72 * n))
 
     def gen_load_update_XImats_helpers(self, use_thread_group=False):
-        self.gen_add_func_doc("Kept for API compatibility: X(q) is computed inside the traced programs", [],
-                              ["s_XImats unused", "s_q unused", "d_robotModel unused", "s_temp unused"], None)
-        self.gen_add_code_lines(["template <typename T>", "__device__",
-                                 "void load_update_XImats_helpers(T *s_XImats, const T *s_q, "
-                                 "const robotModel<T> *d_robotModel, T *s_temp) {}", ""])
+        """X_i(q) for every joint into s_XImats (and the I block and topology table copied beside it): what
+        reference helpers/_topology_helpers.py:90-182 emits, with every q-dependent entry written by the
+        thread that owns the joint instead of thread 0."""
+        n = self.robot.get_num_pos()
+        topo = self._needs_topology_param()
+        params = ["s_XImats is the (shared) memory destination location for the XImats (72*NUM_JOINTS)",
+                  "s_q is the (shared) memory location of the current configuration",
+                  "d_robotModel is the pointer to the initialized model specific helpers",
+                  "s_temp is temporary (shared) memory for sin and cos of size: %d" % (2 * n)]
+        if topo:
+            params.insert(2, "s_topology_helpers is the (shared) memory destination location for the topology_helpers")
+        self.gen_add_func_doc("Updates the Xmats in (shared) GPU memory acording to the configuration", [], params, None)
+        if topo:
+            self.gen_add_code_line("#define GRID_XIMATS_TAKES_TOPOLOGY_HELPERS 1   // extra int *s_topology_helpers argument")
+        lines = ["template <typename T>", "__device__",
+                 "void load_update_XImats_helpers(T *s_XImats, const T *s_q, %sconst robotModel<T> *d_robotModel, "
+                 "T *s_temp) {" % ("int *s_topology_helpers, " if topo else ""),
+                 "    const int tid_ = threadIdx.x + threadIdx.y*blockDim.x, nthr_ = blockDim.x*blockDim.y;",
+                 "    for(int ind = tid_; ind < %d; ind += nthr_){ s_XImats[ind] = d_robotModel->d_XImats[ind]; }" % (72 * n)]
+        if topo:
+            lines.append("    for(int ind = tid_; ind < %d; ind += nthr_){ s_topology_helpers[ind] = "
+                         "d_robotModel->d_topology_helpers[ind]; }" % self.gen_topology_helpers_size())
+        lines += ["    for(int k = tid_; k < %d; k += nthr_){ s_temp[k] = static_cast<T>(sin(s_q[k])); "
+                  "s_temp[k+%d] = static_cast<T>(cos(s_q[k])); }" % (n, n),
+                  "    __syncthreads();",
+                  "    for(int k = tid_; k < %d; k += nthr_){" % n,
+                  "        const T sn_ = s_temp[k], cs_ = s_temp[k+%d], th_ = s_q[k]; T *X_ = &s_XImats[36*k];" % n,
+                  "        (void)sn_; (void)cs_; (void)th_;",
+                  "        switch(k){"]
+        for i, ent in enumerate(self._ximats_entries()):
+            lines.append("        case %d:" % i)
+            rev = self.robot.S_ind[i] < 3
+            for col in range(6):
+                for row in range(6):
+                    a, b, c = ent[(row, col)]
+                    if a == 0.0 and b == 0.0:
+                        continue
+                    terms = []
+                    if a != 0.0:
+                        terms.append("static_cast<T>(%r)*%s" % (a, "sn_" if rev else "th_"))
+                    if b != 0.0:
+                        terms.append("static_cast<T>(%r)*cs_" % b)
+                    if c != 0.0:
+                        terms.append("static_cast<T>(%r)" % c)
+                    lines.append("            X_[%d] = %s;" % (6 * col + row, " + ".join(terms)))
+            lines.append("            break;")
+        lines += ["        }", "    }", "    __syncthreads();", "}", ""]
+        self.gen_add_code_lines(lines)
 
     def gen_init_close_grid(self):
         if None in self._family.values():
@@ -555,7 +676,10 @@ class GRiDCodeGenerator:
         self.gen_add_func_doc("Frees the memory used by grid", [],
                               ["streams allocated by init_grid", "robotModel allocated by init_robotModel",
                                "data allocated by init_gridData"], None)
-        frees = ["    gpuErrchk(cudaFree(d_robotModel));"]
+        frees = ["    robotModel<T> h_robotModel; gpuErrchk(cudaMemcpy(&h_robotModel,d_robotModel,sizeof(robotModel<T>),"
+                 "cudaMemcpyDeviceToHost));",
+                 "    gpuErrchk(cudaFree(h_robotModel.d_XImats)); gpuErrchk(cudaFree(h_robotModel.d_topology_helpers));",
+                 "    gpuErrchk(cudaFree(d_robotModel));"]
         for nm in ("q_qd_u", "q_qd", "q", "c", "Minv", "qdd", "dc_du", "df_du"):
             frees.append("    gpuErrchk(cudaFree(hd_data->d_%s)); gpuErrchk(cudaFreeHost(hd_data->h_%s));" % (nm, nm))
         self.gen_add_code_lines(["template <typename T>", "__host__",

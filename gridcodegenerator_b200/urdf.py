@@ -2,9 +2,18 @@
 
 Replaces the external URDFParser package (reference README.md:8, not vendored)
 for the subset the reference supports: a fixed base, 1-DoF revolute /
-continuous / prismatic joints about a positive principal axis, fixed joints
-merged into their parent link, joint ids assigned in DFS pre-order
-(SURVEY.md section 8c "Implicit invariants").
+continuous / prismatic joints, fixed joints merged into their parent link, joint
+ids assigned in DFS pre-order (SURVEY.md section 8c "Implicit invariants").
+
+The reference needs a ONE-HOT motion subspace S (helpers/_topology_helpers.py:247 takes
+``S.tolist().index(1)``), i.e. a joint about a positive principal axis of its own frame.
+Real URDFs also use negative axes (``0 -1 0``: half of the Atlas arm joints) and, rarely,
+skew ones.  Such a joint keeps its meaning and gets a one-hot S by re-defining the child
+frame: with R_a the rotation that takes the URDF axis a onto the nearest positive principal
+axis e_k, the joint frame F is replaced by F' = R_a F (tree transform E0' = R_a E0, same
+origin), and everything that hangs off the child link - its inertia, fixed children, the
+origins of the next joints - is expressed in F' through the constant transform F' -> F.
+q keeps the URDF's sign convention.
 """
 from __future__ import annotations
 
@@ -45,6 +54,32 @@ def _link_inertia(link) -> np.ndarray:
                    [g("ixz"), g("iyz"), g("izz")]])
     Rc = rpy_to_R(rpy)
     return spatial_inertia(mass, xyz, Rc @ Ic @ Rc.T)
+
+
+def axis_alignment(axis) -> tuple:
+    """(k, R_a): principal axis index k and the rotation with R_a @ a = e_k for the unit vector a = axis/|axis|.
+    k is the component of largest magnitude; a negative one is first flipped by a half turn about the
+    next principal axis (exact for the common ``0 -1 0`` case), the rest is the minimal rotation."""
+    a = np.asarray(axis, dtype=np.float64)
+    nrm = np.linalg.norm(a)
+    if nrm < 1e-12:
+        raise ValueError("zero joint axis")
+    a = a / nrm
+    k = int(np.argmax(np.abs(a)))
+    F = np.eye(3)
+    if a[k] < 0:
+        m = (k + 1) % 3
+        F = -np.eye(3)
+        F[m, m] = 1.0                      # half turn about e_m: det = +1, e_k -> -e_k
+    a1 = F @ a
+    t = np.zeros(3)
+    t[k] = 1.0
+    v, c = np.cross(a1, t), float(a1 @ t)
+    vx = np.array([[0.0, -v[2], v[1]], [v[2], 0.0, -v[0]], [-v[1], v[0], 0.0]])
+    R2 = np.eye(3) + vx + vx @ vx / (1.0 + c)          # c = |a_k| >= 1/sqrt(3)
+    R = R2 @ F
+    R[np.abs(R) < 1e-15] = 0.0
+    return k, R
 
 
 def parse_urdf_string(text: str, name: Optional[str] = None) -> Robot:
@@ -93,15 +128,12 @@ def parse_urdf_string(text: str, name: Optional[str] = None) -> Robot:
                 raise NotImplementedError("joint type %r is not supported" % jtype)
             ax = j.find("axis")
             axis = _floats(ax.get("xyz") if ax is not None else None, [1, 0, 0])
-            hot = [k for k in range(3) if abs(axis[k] - 1.0) < 1e-9]
-            if len(hot) != 1 or abs(np.abs(axis).sum() - 1.0) > 1e-9:
-                raise NotImplementedError(
-                    "joint %s: only positive principal axes are supported (S must be one-hot, "
-                    "reference helpers/_topology_helpers.py:247), got %r" % (j.get("name"), axis.tolist()))
+            k_axis, R_a = axis_alignment(axis)              # identity for a positive principal axis
+            X_T = xform(R_a, np.zeros(3)) @ X_T             # joint frame F -> F' = R_a F (same origin)
             dyn = j.find("dynamics")
             jid = len(parent)
             parent.append(owner)
-            S_ind.append(hot[0] + (3 if jtype == "prismatic" else 0))
+            S_ind.append(k_axis + (3 if jtype == "prismatic" else 0))
             # recover (E, r) of the composed tree transform
             E = X_T[:3, :3]
             rx = -E.T @ X_T[3:, :3]
@@ -111,7 +143,7 @@ def parse_urdf_string(text: str, name: Optional[str] = None) -> Robot:
             damping.append(float(dyn.get("damping", "0")) if dyn is not None else 0.0)
             jnames.append(j.get("name"))
             lnames.append(child)
-            visit(child, jid, np.eye(6))
+            visit(child, jid, xform(R_a.T, np.zeros(3)))    # the child link lives in F: F' -> F
 
     visit(roots[0], -1, np.eye(6))
     return Robot(name or root.get("name", "robot"), parent, S_ind, E0, r0, Imats, damping,

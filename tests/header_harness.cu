@@ -5,9 +5,27 @@
 // output: c, c_qdd, Minv, fd_qdd, dc_du, dc_du_qdd, df_du, df_du_pre, df_du_compute_only  (N states each)
 //         then device-function results for state 0: df_du_dev, dc_du_inner, Minv_inner, qdd_finish, c_inner,
 //         mxX(v1, k) for k = 0..5 (column 2 tripled), fx_times_v(v1, f1), fx(v1) * f1 via dot_prod
+//         last (every robot): s_XImats (72 n) after load_update_XImats_helpers on state 0
 #include "grid.cuh"
 #include <vector>
 using namespace grid;
+
+// what a third-party kernel written against grid.cuh does first: X_i(q), I_i into shared memory
+template <typename T>
+__global__ void ximats_kernel(T *out, const T *q_qd_u, const robotModel<T> *d_robotModel) {
+    constexpr int n = NUM_JOINTS;
+    extern __shared__ T s_dyn[];
+    T *s_XImats = s_dyn, *s_q = s_XImats + 72 * n, *s_temp = s_q + n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_q[i] = q_qd_u[i];
+    __syncthreads();
+#ifdef GRID_XIMATS_TAKES_TOPOLOGY_HELPERS
+    __shared__ int s_topology_helpers[8 * n];
+    load_update_XImats_helpers<T>(s_XImats, s_q, s_topology_helpers, d_robotModel, s_temp);
+#else
+    load_update_XImats_helpers<T>(s_XImats, s_q, d_robotModel, s_temp);
+#endif
+    for (int i = threadIdx.x; i < 72 * n; i += blockDim.x) out[i] = s_XImats[i];
+}
 
 #ifdef HARNESS_DEVICE_FNS
 template <typename T>
@@ -113,6 +131,16 @@ int main(int argc, char **argv) {
     dump(dev.data(), dev_words);
     cudaFree(d_dev);
 #endif
+    {
+        float *d_xi;
+        gpuErrchk(cudaMalloc(&d_xi, 72 * n * sizeof(float)));
+        ximats_kernel<float><<<1, 96, (72 * n + 3 * n) * sizeof(float)>>>(d_xi, hd->d_q_qd_u, d_robotModel);
+        gpuErrchk(cudaDeviceSynchronize());
+        std::vector<float> xi(72 * n);
+        gpuErrchk(cudaMemcpy(xi.data(), d_xi, xi.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        dump(xi.data(), xi.size());
+        cudaFree(d_xi);
+    }
     fclose(o);
     close_grid<float>(streams, d_robotModel, hd);
     printf("ok N=%d n=%d\n", N, n);

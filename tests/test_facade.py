@@ -199,7 +199,16 @@ def test_emitted_header_host_and_device_functions_on_gpu(tmp_path, name, N):
     assert relerr(df[S], ref_fd_grad) < TOL["fd_grad"]
     assert relerr(take(2 * n * n)[S], ref_fd_grad) < TOL["fd_grad"]          # USE_QDD_MINV_FLAG
     assert np.array_equal(take(2 * n * n), df)                                # _compute_only
+    def check_ximats():
+        """s_XImats after load_update_XImats_helpers(state 0): [X_0(q_0) .. | I_0 ..], column-major 6x6 each
+        (reference helpers/_topology_helpers.py:19-47, 90-182), against the robot's own X(q) and inertias."""
+        xi = take(72 * n, 1)[0].reshape(2 * n, 6, 6).transpose(0, 2, 1)
+        for i in range(n):
+            assert np.allclose(xi[i], robot.get_Xmat_Func_by_id(i)(q64[0, i]), rtol=1e-5, atol=1e-6), i
+            assert np.allclose(xi[n + i], robot.get_Imat_by_id(i), rtol=1e-6, atol=1e-7), i
+
     if name != "iiwa14":
+        check_ximats()
         assert pos == data.size
         return
     # device functions on state 0 (the last host call left FD's qdd in d_qdd)
@@ -217,4 +226,5 @@ def test_emitted_header_host_and_device_functions_on_gpu(tmp_path, name, N):
         assert np.allclose(mx[k], expect, rtol=1e-4, atol=1e-5), k
     assert np.allclose(take(6, 1)[0], O.cross_force(v[:, 1], f[:, 1]), rtol=1e-4, atol=1e-4)
     assert np.allclose(take(6, 1)[0], O.cross_force(v[:, 1], f[:, 1]), rtol=1e-4, atol=1e-4)
+    check_ximats()
     assert pos == data.size

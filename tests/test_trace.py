@@ -40,6 +40,12 @@ def _run(robot, key, q, qd, u, qdd, dtype):
         Md = np.array([O.minv(robot, q[s]) for s in range(N)])
         return (p.evaluate(_ins(q=q, qd=qd, qdd=qdd, Minv=Mu), dtype)["df_du"],
                 O.batch(robot, "fd_grad_qdd_minv", q, qd, qdd, Minv_in=Md), "fd_grad")
+    if key in ("fd_vjp", "fd_lin"):              # consumers fused after the FD gradient
+        lam = np.random.default_rng(2).uniform(-3, 3, (N, 2 * robot.n))
+        ins = _ins(q=q, qd=qd, u=u, lam=lam)
+        ins["dt"] = 0.0125
+        ins = {k: v for k, v in ins.items() if k in p.inputs}
+        return p.evaluate(ins, dtype)[key], O.consumer_batch(robot, key, q, qd, u, 0.0125, lam), "fd_grad"
     raise KeyError(key)
 
 

@@ -81,9 +81,97 @@ def test_fixed_joint_merging_and_conventions():
     assert np.allclose(r.Xmat(0, 0.6), XJ @ xform(r.E0[0], r.r0[0]))
 
 
+def _urdf_fk(text, q):
+    """World pose (R, p) of every moving joint's URDF child frame by plain URDF semantics:
+    T_child = T_parent * T_origin * Rot(axis, q)  or  * Trans(axis * q) - independent of Robot/xform."""
+    import xml.etree.ElementTree as ET
+    root = ET.fromstring(text)
+    joints = {j.find("child").get("link"): j for j in root.findall("joint")}
+    order = [j for j in root.findall("joint")]
+    pose = {}
+    children = {l.get("name") for l in root.findall("link")} - set(joints)
+    base = children.pop()
+    pose[base] = (np.eye(3), np.zeros(3))
+    out, qi = [], 0
+    pending = list(order)
+    while pending:
+        for j in list(pending):
+            par = j.find("parent").get("link")
+            if par not in pose:
+                continue
+            pending.remove(j)
+            Rp, pp = pose[par]
+            o = j.find("origin")
+            xyz = np.array([float(t) for t in (o.get("xyz") or "0 0 0").split()]) if o is not None else np.zeros(3)
+            rpy = [float(t) for t in (o.get("rpy") or "0 0 0").split()] if o is not None else [0, 0, 0]
+            R, p = Rp @ rpy_to_R(rpy), pp + Rp @ xyz
+            if j.get("type") != "fixed":
+                a = np.array([float(t) for t in j.find("axis").get("xyz").split()])
+                a = a / np.linalg.norm(a)
+                if j.get("type") == "prismatic":
+                    p = p + R @ (a * q[qi])
+                else:
+                    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+                    R = R @ (np.eye(3) + np.sin(q[qi]) * K + (1 - np.cos(q[qi])) * K @ K)
+                out.append((qi, R, p))
+                qi += 1
+            pose[j.find("child").get("link")] = (R, p)
+    return out
+
+
+SKEW = URDF.replace('<axis xyz="0 1 0"/>', '<axis xyz="0 -1 0"/>').replace('<axis xyz="0 0 1"/>', '<axis xyz="0.2 -0.3 0.9"/>')
+
+
+@pytest.mark.parametrize("text", [URDF, SKEW, URDF.replace('<axis xyz="0 0 1"/>', '<axis xyz="-1 0 0"/>')])
+def test_negative_and_skew_axes_keep_the_urdf_kinematics(text):
+    """Joints about negative / non-principal axes get a one-hot S by re-defining the child frame
+    (gridcodegenerator_b200/urdf.py): the frame origins and the joint axes in the world must be exactly what
+    plain URDF forward kinematics gives, for the URDF's own sign of q."""
+    from gridcodegenerator_b200.urdf import axis_alignment
+    r = parse_urdf_string(text)
+    assert all(0 <= k < 6 for k in r.S_ind) and r.n == 2
+    q = np.array([0.7, -0.4])
+    fk = _urdf_fk(text, q)
+    X = np.eye(6)
+    for i, R_w, p_w in fk:                            # serial chain j0 -> j1
+        X = r.Xmat(i, q[i]) @ X                       # base -> F'_i
+        E = X[:3, :3]
+        rx = -E.T @ X[3:, :3]
+        assert np.allclose([rx[2, 1], rx[0, 2], rx[1, 0]], p_w, atol=1e-12)       # frame origin in the world
+        k = r.S_ind[i] % 3
+        import xml.etree.ElementTree as ET
+        axes = [np.array([float(t) for t in j.find("axis").get("xyz").split()]) for j in ET.fromstring(text).findall("joint")
+                if j.get("type") != "fixed"]
+        a_w = R_w @ (axes[i] / np.linalg.norm(axes[i]))
+        assert np.allclose(E.T[:, k], a_w, atol=1e-12)                             # e_k of F' is the URDF axis
+        kk, R_a = axis_alignment(axes[i])
+        assert kk == k and np.allclose(R_a.T @ E, R_w.T, atol=1e-12)               # F' = R_a F
+        assert np.isclose(np.linalg.det(R_a), 1.0)
+
+
+def test_flipped_axis_is_the_mirrored_joint():
+    """axis -e_y with q is the same mechanism as axis +e_y with -q: equal inverse dynamics up to the sign of
+    that joint's torque (checked through the oracle-independent traced RNEA)."""
+    from gridcodegenerator_b200.algorithms import TRACERS
+    a = parse_urdf_string(URDF.replace('<axis xyz="0 1 0"/>', '<axis xyz="0 -1 0"/>'))
+    b = parse_urdf_string(URDF)
+    rng = np.random.default_rng(0)
+    q, qd, qdd = rng.uniform(-1, 1, (3, 2))
+    sgn = np.array([-1.0, 1.0])
+
+    def rnea(robot, q, qd, qdd):
+        ins = {"gravity": np.array([9.81])}
+        for i in range(2):
+            ins["q%d" % i], ins["qd%d" % i], ins["qdd%d" % i] = (np.array([x[i]]) for x in (q, qd, qdd))
+        return TRACERS["id_qdd"](robot).evaluate(ins)["c"][0]
+
+    ca, cb = rnea(a.with_damping(0.0), q, qd, qdd), rnea(b.with_damping(0.0), sgn * q, sgn * qd, sgn * qdd)
+    assert np.allclose(ca, sgn * cb, atol=1e-12)
+
+
 def test_unsupported_urdfs_fail_loudly():
-    with pytest.raises(NotImplementedError):
-        parse_urdf_string(URDF.replace('<axis xyz="0 1 0"/>', '<axis xyz="0 -1 0"/>'))
+    with pytest.raises(ValueError):
+        parse_urdf_string(URDF.replace('<axis xyz="0 1 0"/>', '<axis xyz="0 0 0"/>'))
     with pytest.raises(NotImplementedError):
         parse_urdf_string(URDF.replace('type="prismatic"', 'type="floating"'))
     with pytest.raises(ValueError):
