@@ -109,11 +109,11 @@ def run_reference_arm(a):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     with mp.get_context("fork").Pool(cores) as pool:
         rate = 0.0
-        for _ in range(max(1, min(a.warmup, 2))):
-            rate, _, _ = cpu_reference_pass(a.robot, a.alg, cores * 8, cores, pool)
-        budget_s = 8.0
+        for w in range(max(1, min(a.warmup, 2))):          # the first pass also pays imports and the robot load
+            rate, _, _ = cpu_reference_pass(a.robot, a.alg, cores * (8 if w == 0 else 64), cores, pool)
+        budget_s = 10.0
         sample = a.cpu_sample or int(min(a.batch, max(cores, rate * budget_s)))
-        if sample >= a.batch * 0.9:
+        if sample >= a.batch * 0.8:
             sample = a.batch
         vals, t0, done, ms1 = [], time.perf_counter(), 0, 0.0
         for _ in range(a.steps):

@@ -200,10 +200,12 @@ def rnea(sr: SymRobot, qd: Sequence[V], qdd: Optional[Sequence[V]], gravity: V) 
 
 
 # ---- Minv ---------------------------------------------------------------------------
-def minv(sr: SymRobot, bpass: Optional[dict] = None) -> Dict[Tuple[int, int], V]:
+def minv(sr: SymRobot, bpass: Optional[dict] = None, on_final=None) -> Dict[Tuple[int, int], V]:
     """Upper-triangular M^-1 as {(row, col): V}, col >= row.  `bpass` (a dict) receives the state
     after the backward pass - Minv entries, F columns, U, Dinv - i.e. what the reference's
-    test_minv_bpass returns (_test.py:117-184)."""
+    test_minv_bpass returns (_test.py:117-184).  `on_final(i, j, m)` is called the moment entry (i, j)
+    has its final value, so that consumers (qdd = Minv (u - c), ...) can use it right there in the trace:
+    an entry that is consumed where it is produced does not occupy a register until the end of the pass."""
     p, robot, n = sr.p, sr.robot, sr.n
     zero6 = lambda: zeros(p, 6)
     Mi: Dict[Tuple[int, int], V] = {}
@@ -246,6 +248,8 @@ def minv(sr: SymRobot, bpass: Optional[dict] = None) -> Dict[Tuple[int, int], V]
         for j in cols:
             m = Mi.get((i, j), p.const(0.0))
             Mi[(i, j)] = m
+            if on_final is not None:
+                on_final(i, j, m)
             Fij = zero6()
             Fij[k] = m
             if par >= 0 and F[par].get(j) is not None:
@@ -256,6 +260,43 @@ def minv(sr: SymRobot, bpass: Optional[dict] = None) -> Dict[Tuple[int, int], V]
 
 def minv_get(Mi: Dict[Tuple[int, int], V], r: int, c: int) -> V:
     return Mi[(r, c)] if r <= c else Mi[(c, r)]
+
+
+class SymmetricProduct:
+    """y = Minv x accumulated entry by entry in the order the Minv pass finalises its upper triangle
+    (use as minv(..., on_final=acc)): y_i += M_ij x_j and, off the diagonal, y_j += M_ij x_i."""
+
+    def __init__(self, p: Program, x: Sequence[V]):
+        self.p, self.x = p, list(x)
+        self.y: List[Optional[V]] = [None] * len(self.x)
+
+    def _add(self, i: int, term: V):
+        self.y[i] = term if self.y[i] is None else self.y[i] + term
+
+    def __call__(self, i: int, j: int, m: V):
+        self._add(i, m * self.x[j])
+        if j != i:
+            self._add(j, m * self.x[i])
+
+    def result(self) -> List[V]:
+        return [self.p.const(0.0) if v is None else v for v in self.y]
+
+
+def fd_prologue(sr: SymRobot, qd: Sequence[V], u: Sequence[V], gravity: V, extra: Sequence[Sequence[V]] = ()):
+    """The common head of FD and the FD gradient (algorithms/_forward_dynamics_gradient.py:9-20): bias forces
+    c = RNEA(q, qd, 0), Minv, qdd = Minv (u - c).  The product rides on the Minv pass (SymmetricProduct).
+    `extra`: more vectors to multiply by Minv in the same pass (the costate part lam_v of the fused VJP).
+    Returns (R0, Mi, qdd, [Minv x for x in extra])."""
+    p, n = sr.p, sr.n
+    R0 = rnea(sr, qd, None, gravity)
+    acc = [SymmetricProduct(p, [u[i] - R0.c[i] for i in range(n)])] + [SymmetricProduct(p, x) for x in extra]
+
+    def on_final(i, j, m):
+        for a in acc:
+            a(i, j, m)
+
+    Mi = minv(sr, on_final=on_final)
+    return R0, Mi, acc[0].result(), [a.result() for a in acc[1:]]
 
 
 # ---- RNEA gradient -------------------------------------------------------------------
@@ -278,7 +319,8 @@ class _DirectSource:
         return cross_motion_axis(self.p, self.robot.S_ind[i], self.R.f[i])
 
 
-def rnea_grad_columns(sr: SymRobot, qd: Sequence[V], R: Optional[RneaResult], src=None, joints=None, record=None):
+def rnea_grad_columns(sr: SymRobot, qd: Sequence[V], R: Optional[RneaResult], src=None, joints=None, record=None,
+                      sides: Sequence[int] = (0, 1)):
     """Yields (j, dc_dq_col, dc_dqd_col) one du-column pair at a time; each col is a
     dict {row i: V} over anc(j) | sub(j) (structural zeros elsewhere).  Columns are
     independent through both passes, which is what lets the emitter finish and store
@@ -286,8 +328,11 @@ def rnea_grad_columns(sr: SymRobot, qd: Sequence[V], R: Optional[RneaResult], sr
     the per-joint state data v, I v, mxS(X a_parent), mxS(f) come from; `joints` restricts
     the columns (pipeline.py traces one group of columns per program).  `record(j, name, i, s, vec)`
     is called with the per-joint intermediates of column j (names "dv", "da", "df_fp", "df": the arrays
-    the reference's test_rnea_grad_inner returns, _test.py:229-488)."""
+    the reference's test_rnea_grad_inner returns, _test.py:229-488).  `sides` = (0,) or (1,) computes only
+    the d/dq or only the d/dqd column of each joint (the other one is yielded as None): the two recursions
+    share nothing but the state data, which lets pipeline.py halve a column program that is too long."""
     p, robot, n = sr.p, sr.robot, sr.n
+    sides = tuple(sides)
     if src is None:
         src = _DirectSource(p, robot, R)
     for j in (range(n) if joints is None else joints):
@@ -300,18 +345,20 @@ def rnea_grad_columns(sr: SymRobot, qd: Sequence[V], R: Optional[RneaResult], sr
             k = robot.S_ind[i]
             vi, Ivi = src.v(i), src.Iv(i)
             if i == j:
-                dv[0][i] = cross_motion_axis(p, k, vi)                  # == mxS(X v_parent)
-                e = zeros(p, 6)
-                e[k] = p.const(1.0)
-                dv[1][i] = e
-                da[0][i] = vadd(cross_motion_axis(p, k, dv[0][i], qd[i]), src.mxs_Xa(i))
-                da[1][i] = cross_motion_axis(p, k, vi)
+                if 0 in sides:
+                    dv[0][i] = cross_motion_axis(p, k, vi)              # == mxS(X v_parent)
+                    da[0][i] = vadd(cross_motion_axis(p, k, dv[0][i], qd[i]), src.mxs_Xa(i))
+                if 1 in sides:
+                    e = zeros(p, 6)
+                    e[k] = p.const(1.0)
+                    dv[1][i] = e
+                    da[1][i] = cross_motion_axis(p, k, vi)
             else:
                 par = robot.parent[i]
-                for s in (0, 1):
+                for s in sides:
                     dv[s][i] = sr.X_motion(i, dv[s][par])
                     da[s][i] = vadd(sr.X_motion(i, da[s][par]), cross_motion_axis(p, k, dv[s][i], qd[i]))
-            for s in (0, 1):
+            for s in sides:
                 df[s][i] = vadd(vadd(sr.I_mul(i, da[s][i]), cross_force(dv[s][i], Ivi)),
                                 cross_force(vi, sr.I_mul(i, dv[s][i])))
                 if record is not None:
@@ -321,25 +368,26 @@ def rnea_grad_columns(sr: SymRobot, qd: Sequence[V], R: Optional[RneaResult], sr
         cols = ({}, {})
         for i in reversed(sub):
             par = robot.parent[i]
-            for s in (0, 1):
+            for s in sides:
                 cols[s][i] = df[s][i][robot.S_ind[i]]
                 if record is not None:
                     record(j, "df", i, s, df[s][i])
             if i != j:
-                for s in (0, 1):
+                for s in sides:
                     df[s][par] = vadd(df[s][par], sr.XT_force(i, df[s][i]))
         # leave the subtree: the dq column also carries -X_j^T (f_j x) S_j
-        up = [vsub(df[0][j], src.mxs_f(j)), df[1][j]]
+        up = [vsub(df[0][j], src.mxs_f(j)) if 0 in sides else None, df[1][j] if 1 in sides else None]
         i = j
         while robot.parent[i] >= 0:
-            up = [sr.XT_force(i, up[0]), sr.XT_force(i, up[1])]
+            up = [sr.XT_force(i, up[s]) if s in sides else None for s in (0, 1)]
             i = robot.parent[i]
-            for s in (0, 1):
+            for s in sides:
                 cols[s][i] = up[s][robot.S_ind[i]]
                 if record is not None:
                     record(j, "df", i, s, up[s])
-        cols[1][j] = cols[1][j] + robot.damping[j]
-        yield j, cols[0], cols[1]
+        if 1 in sides:
+            cols[1][j] = cols[1][j] + robot.damping[j]
+        yield j, (cols[0] if 0 in sides else None), (cols[1] if 1 in sides else None)
 
 
 # ---- traced programs -------------------------------------------------------------------
@@ -376,11 +424,9 @@ def trace_fd(robot: Robot) -> Program:
     q, qd, u = _inputs(p, n, ("q", "qd", "u"))
     g = p.inp("gravity")
     sr = SymRobot(p, robot, q)
-    R = rnea(sr, qd, None, g)
-    Mi = minv(sr)
-    umc = [u[i] - R.c[i] for i in range(n)]
+    _, _, qdd, _ = fd_prologue(sr, qd, u, g)
     for i in range(n):
-        p.output("qdd", i, dot([minv_get(Mi, i, j) for j in range(n)], umc))
+        p.output("qdd", i, qdd[i])
     return p
 
 
@@ -415,10 +461,7 @@ def trace_fd_grad(robot: Robot, use_qdd_minv: bool = False) -> Program:
         Mi = {(r, c): p.inp("Minv%d" % (c * n + r)) for r in range(n) for c in range(r, n)}
     else:
         (u,) = _inputs(p, n, ("u",))
-        R0 = rnea(sr, qd, None, g)
-        Mi = minv(sr)
-        umc = [u[i] - R0.c[i] for i in range(n)]
-        qdd = [dot([minv_get(Mi, i, j) for j in range(n)], umc) for i in range(n)]
+        _, Mi, qdd, _ = fd_prologue(sr, qd, u, g)
     R = rnea(sr, qd, qdd, g)
     for j, cq, cqd in rnea_grad_columns(sr, qd, R):
         for s, col in ((0, cq), (1, cqd)):
@@ -449,12 +492,16 @@ def consumer_out_words(alg: str, n: int) -> int:
 
 
 def vjp_column(p: Program, cq: Dict[int, V], cqd: Dict[int, V], w: Sequence[V], lam_q_j: V, lam_v_j: V, dt: V):
-    """(A^T lam)[j], (A^T lam)[n + j] from the dc_du columns of joint j and w = Minv lam_v."""
-    rows = sorted(cq)
-    gq = dot([cq[r] for r in rows], [w[r] for r in rows])
-    rows = sorted(cqd)
-    gqd = dot([cqd[r] for r in rows], [w[r] for r in rows])
-    return lam_q_j - dt * gq, lam_v_j + dt * (lam_q_j - gqd)
+    """(A^T lam)[j], (A^T lam)[n + j] from the dc_du columns of joint j and w = Minv lam_v (a column that was not
+    computed - None - gives None)."""
+    aq = av = None
+    if cq is not None:
+        rows = sorted(cq)
+        aq = lam_q_j - dt * dot([cq[r] for r in rows], [w[r] for r in rows])
+    if cqd is not None:
+        rows = sorted(cqd)
+        av = lam_v_j + dt * (lam_q_j - dot([cqd[r] for r in rows], [w[r] for r in rows]))
+    return aq, av
 
 
 def trace_fd_consumer(robot: Robot, alg: str) -> Program:
@@ -464,17 +511,14 @@ def trace_fd_consumer(robot: Robot, alg: str) -> Program:
     q, qd, u = _inputs(p, n, ("q", "qd", "u"))
     g, dt = p.inp("gravity"), p.inp("dt")
     sr = SymRobot(p, robot, q)
-    R0 = rnea(sr, qd, None, g)
-    Mi = minv(sr)
-    umc = [u[i] - R0.c[i] for i in range(n)]
-    qdd = [dot([minv_get(Mi, i, j) for j in range(n)], umc) for i in range(n)]
+    lam = [p.inp("lam%d" % i) for i in range(2 * n)] if alg == "fd_vjp" else None
+    _, Mi, qdd, extra = fd_prologue(sr, qd, u, g, [lam[n:]] if lam else [])
     R = rnea(sr, qd, qdd, g)
     for i in range(n):
         p.output(alg, i, q[i] + dt * qd[i])
         p.output(alg, n + i, qd[i] + dt * qdd[i])
     if alg == "fd_vjp":
-        lam = [p.inp("lam%d" % i) for i in range(2 * n)]
-        w = [dot([minv_get(Mi, i, j) for j in range(n)], lam[n:]) for i in range(n)]
+        w = extra[0]
         for j, cq, cqd in rnea_grad_columns(sr, qd, R):
             aq, av = vjp_column(p, cq, cqd, w, lam[j], lam[n + j], dt)
             p.output(alg, 2 * n + j, aq)
@@ -686,10 +730,7 @@ def trace_column_program(robot: Robot, alg: str, use_qdd: bool = False) -> Progr
     Mi = None
     if alg == "fd_grad":
         (u,) = _inputs(p, n, ("u",))
-        R0 = rnea(sr, qd, None, g)
-        Mi = minv(sr)
-        umc = [u[i] - R0.c[i] for i in range(n)]
-        qdd = [dot([minv_get(Mi, i, j) for j in range(n)], umc) for i in range(n)]
+        _, Mi, qdd, _ = fd_prologue(sr, qd, u, g)
     else:
         qdd = _inputs(p, n, ("qdd",))[0] if use_qdd else None
     R = rnea(sr, qd, qdd, g)
@@ -824,10 +865,7 @@ def trace_fd_grad_paired(robot: Robot, use_qdd_minv: bool = False, park: Sequenc
         Mi = {(r, c): p.inp("Minv%d" % (c * n + r)) for r in range(n) for c in range(r, n)}
     else:
         (u,) = _inputs(p, n, ("u",))
-        R0 = rnea(sr, qd, None, g)
-        Mi = minv(sr)
-        umc = [u[i] - R0.c[i] for i in range(n)]
-        qdd = [dot([minv_get(Mi, i, j) for j in range(n)], umc) for i in range(n)]
+        _, Mi, qdd, _ = fd_prologue(sr, qd, u, g)
     R = rnea(sr, qd, qdd, g)
     src = ColumnSource(sr, R, park)
     Mh = {k: p.park(v) for k, v in Mi.items()} if "Minv" in park else None

@@ -462,6 +462,7 @@ def emit_wps_tables(robot: Robot, lay: Dict[str, object], include: bool = True) 
     t = ["namespace GRID_NS { namespace gen {\n", "struct WT {\n"]
     for k in ("N", "NT", "NSLOT", "NSAVE", "DF_WORDS", "IA_LANE0", "RNEA_TID", "COL_WARPS", "NLEVELS"):
         t.append("    static constexpr int %s = %d;\n" % (k, lay[k]))
+    t.append("    static constexpr bool TC_MATMUL = %s;\n" % ("true" if lay.get("TC_MATMUL") else "false"))
     t.append("};\n")
     t.append(ints("wt_parent", robot.parent))
     t.append(ints("wt_S", robot.S_ind))
@@ -518,11 +519,18 @@ class KernelPlan:
                  wps_max_states: int = 0, cps_max_states: int = 2048, tps_loop_columns: bool = False,
                  tps_pairs: bool = False, tps_v2_park=None, pipe_algs=None, pipe_min_states: int = 0,
                  pipe_opts: Optional[Dict[str, int]] = None, pipe_min_blocks: Tuple[int, int] = (1, 1),
-                 pipe_warps: int = 8, pipe_sync_every: int = 256, pipe_scratch_lead: int = 160):
+                 pipe_warps: int = 8, pipe_sync_every: int = 256, pipe_scratch_lead: int = 160,
+                 wps_tc_matmul: bool = False, only_algs=None, pipe_small_states: int = 24576,
+                 pipe_small_group_flops: int = 4000, lps_min_states: int = 256, lps_force: bool = False):
         # every constructor argument except the robot: build.py hashes this into the library name, so
         # a library built with one plan is never returned for another
         self._args = {k: v for k, v in locals().items() if k not in ("self", "robot")}
         self.robot = robot
+        # -Minv dc_du of the wide FD-gradient kernel on the tensor cores (3xTF32 mma.sync): measured in
+        # profiles/r2_tc_*; off unless it wins end to end
+        self.wps_tc_matmul = bool(wps_tc_matmul) and robot.n % 16 == 0
+        # experiments: build only these algorithms (the others report "none"); None = all
+        self.only_algs = None if only_algs is None else tuple(only_algs)
         self.tps_warps = tps_warps
         self.tps_sync_every = tps_sync_every if tps_warps > 1 else 0
         self.tps_loop_columns = tps_loop_columns
@@ -531,6 +539,7 @@ class KernelPlan:
         alg = algorithmic_flops(robot)
         self.kind: Dict[str, str] = {}
         self.wps = wps_layout(robot)
+        self.wps["TC_MATMUL"] = self.wps_tc_matmul
         self.wps_ok = self.wps["smem_bytes"] <= 227 * 1024
         # batches up to this many states go to the wide kernel when both exist (latency mode)
         self.wps_max_states = wps_max_states
@@ -538,6 +547,8 @@ class KernelPlan:
             # the dense reference count over-states traced work by ~4x; gate on it
             tps = alg[a] <= tps_max_flops
             wps = self.wps_ok and a != "id"
+            if self.only_algs is not None and a not in self.only_algs:
+                tps = wps = False
             self.kind[a] = "tps+wps" if tps and wps else "tps" if tps else "wps" if wps else "none"
             # latency kernels: gradient algorithms of robots whose 2n columns fit one warp
             if tps and a in ("id_grad", "fd_grad") and 2 * robot.n <= 32:
@@ -558,6 +569,8 @@ class KernelPlan:
             # thread-per-state program exists
             forest = len(components(robot)) > 1
             want = [a for a in self.kind if (forest and a != "id") or "tps" not in self.kind[a]]
+            if self.only_algs is not None:
+                want = [a for a in want if a in self.only_algs]
         else:
             want = list(pipe_algs)
         variants = {"id": ("id", "id_qdd"), "minv": ("minv",), "fd": ("fd",), "id_grad": ("id_grad", "id_grad_qdd"),
@@ -568,10 +581,37 @@ class KernelPlan:
                 for pv in pvs:
                     self.pipe[pv.variant] = pv
                 self.kind[a] = "pipe" if self.kind[a] == "none" else self.kind[a] + "+pipe"
+        # Serial chains whose Minv / FD / gradients have no thread-per-state program (64-link chain): lane-per-state
+        # kernels with rolled joint loops (csrc/grid_lps.cuh) for batches of lps_min_states and more; the
+        # CTA-per-state wide kernels keep the small batches and the USE_QDD_MINV_FLAG overload
+        self.lps_min_states = lps_min_states
+        self.lps = set()
+        if robot.is_serial_chain() and self.wps_ok:
+            for a in ("minv", "fd", "id_grad", "fd_grad"):
+                # lps_force: also for small chains that have thread-per-state programs (test builds: the chain
+                # kernels run on iiwa14 and on a chain with prismatic joints when GRID_FORCE_KERNEL=lps)
+                if "wps" in self.kind[a] and (lps_force or ("tps" not in self.kind[a] and "pipe" not in self.kind[a])):
+                    self.lps.add(a)
+                    self.kind[a] += "+lps"
+        self.lps_forced_only = bool(lps_force)
+        # Second set of FD-gradient column programs for small and mid-size batches (the per-GPU shard when 65 536
+        # states are split over 4-8 GPUs): groups of ~4 k flops instead of 6.5 k give more (task, tiles) items to
+        # spread over the SMs - Atlas 8 192 states 128 vs 152 us, 16 384 states 221 vs 242 us, but 779 vs 737 us at
+        # 65 536 (profiles/r2_atlas_pipe_variants.jsonl).  Only with the default grouping options.
+        self.pipe_small_states = pipe_small_states
+        self.pipe_small = None
+        if ("fd_grad" in self.pipe and self.pipe["fd_grad"].scratch_words > 0 and not self.pipe_opts
+                and pipe_small_states > 0):
+            pv = PipeVariant(robot, "fd_grad", group_flops=pipe_small_group_flops, struct_suffix="Small")
+            if pv.feasible and len(pv.tasks) > len(self.pipe["fd_grad"].tasks):
+                self.pipe_small = pv
         # consumers fused after the FD gradient ride on the family that serves fd_grad at large batches
         self.consumers: Dict[str, str] = {}
         for c in ("fd_vjp", "fd_lin"):
             fams = []
+            if self.only_algs is not None and c not in self.only_algs:
+                self.consumers[c] = "none"
+                continue
             if "tps" in self.kind["fd_grad"]:
                 fams.append("tps")
             if "pipe" in self.kind["fd_grad"]:
@@ -683,7 +723,7 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
             stats["cps_" + nm] = cnt
     if plan.pipe:
         from .pipeline import emit_pipe_struct
-        for v, pv in plan.pipe.items():
+        for v, pv in list(plan.pipe.items()) + ([("fd_grad_small", plan.pipe_small)] if plan.pipe_small else []):
             txt, summ = emit_pipe_struct(pv, plan.pipe_min_blocks, plan.pipe_warps, plan.pipe_sync_every,
                                          plan.pipe_scratch_lead)
             out.append(txt)
@@ -697,15 +737,21 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
     has_wps = lambda a: "wps" in plan.kind[a]
     if any(has_wps(a) for a in plan.kind):
         out.append(emit_wps_tables(robot, plan.wps))
+    if plan.lps:
+        out.append('#include "grid_lps.cuh"\n')
 
     def tps(a, struct):
         if plan.tps_v2_park is not None and a in ("id_grad", "fd_grad"):
             return "tps2_launch<%s, %d, %d>" % (struct, W, plan.min_blocks[a])
         return "tps_launch<%s, %d, %d>" % (struct, W, plan.min_blocks[a])
 
-    def body(a, tps_call, wps_call, cps_call=(), pipe_call=()):
+    def body(a, tps_call, wps_call, cps_call=(), pipe_call=(), lps_call=()):
         """tps_call / wps_call / cps_call: list of (condition or None, expression)."""
         lines = []
+        if a in plan.lps:
+            lines.append("    if (use_lps(N)) {")
+            lines += ["        %sreturn %s;" % ("if (%s) " % c if c else "", e) for c, e in lps_call]
+            lines.append("    }")
         if "cps" in plan.kind[a]:
             lines.append("    if (use_cps(N)) {")
             lines += ["        %sreturn %s;" % ("if (%s) " % c if c else "", e) for c, e in cps_call]
@@ -747,6 +793,11 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
              "    const int f = options().force_kernel;\n"
              "    if (f != kAuto) return f == kPipe;\n"
              "    return N >= %d;\n}" % plan.pipe_min_states)
+    L.append("// serial chains without thread-per-state programs: lane-per-state kernels with rolled joint loops\n"
+             "static bool use_lps(int N) {\n"
+             "    const int f = options().force_kernel;\n"
+             "    if (f != kAuto) return f == kLps;\n"
+             "    return %s;\n}" % ("false" if plan.lps_forced_only else "N >= %d" % plan.lps_min_states))
     G = plan.cps_lanes
     PL = lambda struct, out, inp, in1: "pipe::pipe_launch<gen::%s>(%s, %s, stride, %s, N, g, s)" % (struct, out, inp, in1)
     L.append("cudaError_t launch_id(float *d_c, const float *d_q_qd, int stride, const float *d_qdd, int N, float g,"
@@ -759,12 +810,14 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
     L.append("cudaError_t launch_minv(float *d_Minv, const float *d_q, int stride, int N, cudaStream_t s) {")
     L += body("minv", [(None, "%s(d_Minv, d_q, stride, nullptr, nullptr, N, 0.f, s)" % tps("minv", "AlgMinv"))],
               [(None, "wps::wps_launch<0, false>(d_Minv, d_q, stride, nullptr, nullptr, N, 0.f, s)")],
-              pipe_call=[(None, "pipe::pipe_launch<gen::PipeMinv>(d_Minv, d_q, stride, nullptr, N, 0.f, s)")])
+              pipe_call=[(None, "pipe::pipe_launch<gen::PipeMinv>(d_Minv, d_q, stride, nullptr, N, 0.f, s)")],
+              lps_call=[(None, "lps::lps_launch<0, false>(d_Minv, d_q, stride, nullptr, N, 0.f, s)")])
     L.append("}")
     L.append("cudaError_t launch_fd(float *d_qdd, const float *d_q_qd_u, int stride, int N, float g, cudaStream_t s) {")
     L += body("fd", [(None, "%s(d_qdd, d_q_qd_u, stride, nullptr, nullptr, N, g, s)" % tps("fd", "AlgFd"))],
               [(None, "wps::wps_launch<1, false>(d_qdd, d_q_qd_u, stride, nullptr, nullptr, N, g, s)")],
-              pipe_call=[(None, PL("PipeFd", "d_qdd", "d_q_qd_u", "nullptr"))])
+              pipe_call=[(None, PL("PipeFd", "d_qdd", "d_q_qd_u", "nullptr"))],
+              lps_call=[(None, "lps::lps_launch<1, false>(d_qdd, d_q_qd_u, stride, nullptr, N, g, s)")])
     L.append("}")
     L.append("cudaError_t launch_id_grad(float *d_dc_du, const float *d_q_qd, int stride, const float *d_qdd, int N,"
              " float g, cudaStream_t s) {")
@@ -776,7 +829,9 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
               [("d_qdd", "cps_launch<gen::ColIdGradQdd, %d>(d_dc_du, d_q_qd, stride, d_qdd, N, g, s)" % G),
                (None, "cps_launch<gen::ColIdGrad, %d>(d_dc_du, d_q_qd, stride, nullptr, N, g, s)" % G)],
               pipe_call=[("d_qdd", PL("PipeIdGradQdd", "d_dc_du", "d_q_qd", "d_qdd")),
-                         (None, PL("PipeIdGrad", "d_dc_du", "d_q_qd", "nullptr"))])
+                         (None, PL("PipeIdGrad", "d_dc_du", "d_q_qd", "nullptr"))],
+              lps_call=[("d_qdd", "lps::lps_launch<2, true>(d_dc_du, d_q_qd, stride, d_qdd, N, g, s)"),
+                        (None, "lps::lps_launch<2, false>(d_dc_du, d_q_qd, stride, nullptr, N, g, s)")])
     L.append("}")
     L.append("cudaError_t launch_fd_grad(float *d_df_du, const float *d_in, int stride, const float *d_qdd,"
              " const float *d_Minv, int N, float g, cudaStream_t s) {")
@@ -786,7 +841,9 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
               [("d_qdd", "wps::wps_launch<3, true>(d_df_du, d_in, stride, d_qdd, d_Minv, N, g, s)"),
                (None, "wps::wps_launch<3, false>(d_df_du, d_in, stride, nullptr, nullptr, N, g, s)")],
               [("!d_qdd", "cps_launch<gen::ColFdGrad, %d>(d_df_du, d_in, stride, nullptr, N, g, s)" % G)],
-              pipe_call=[("!d_qdd", PL("PipeFdGrad", "d_df_du", "d_in", "nullptr"))])
+              pipe_call=([("!d_qdd && N <= %d" % plan.pipe_small_states, PL("PipeFdGradSmall", "d_df_du", "d_in", "nullptr"))]
+                         if plan.pipe_small else []) + [("!d_qdd", PL("PipeFdGrad", "d_df_du", "d_in", "nullptr"))],
+              lps_call=[("!d_qdd", "lps::lps_launch<3, false>(d_df_du, d_in, stride, nullptr, N, g, s)")])
     L.append("}")
 
     for c, struct, pstruct, lam in (("fd_vjp", "AlgFdVjp", "PipeFdVjp", "d_lam"), ("fd_lin", "AlgFdLin", "PipeFdLin", "nullptr")):

@@ -41,6 +41,7 @@ static int check_args(const void *out, const void *in, int stride, int min_strid
 
 constexpr int kStreams = 4;
 constexpr int kMinChunk = 2048;      // states; below this, pipelining costs more than it hides
+constexpr size_t kMinChunkBytes = 4u << 20;   // H2D + D2H bytes per chunk
 
 }  // namespace GRID_NS
 
@@ -71,7 +72,7 @@ int grid_set_option(const char *key, const char *value) {
     const bool unset = !value || !*value;
     if (!strcmp(key, "GRID_FORCE_KERNEL")) {
         const int f = GRID_NS::parse_force(value);
-        if (f < 0) return GRID_NS::fail_msg("GRID_FORCE_KERNEL must be tps, wps, cps, pipe or empty");
+        if (f < 0) return GRID_NS::fail_msg("GRID_FORCE_KERNEL must be tps, wps, cps, pipe, lps or empty");
         o.force_kernel = f;
     } else if (!strcmp(key, "GRID_PIPE_MODE")) {
         if (!unset && strcmp(value, "fused") && strcmp(value, "staged"))
@@ -79,6 +80,8 @@ int grid_set_option(const char *key, const char *value) {
         o.pipe_fused = (!unset && !strcmp(value, "fused")) ? 1 : 0;
     } else if (!strcmp(key, "GRID_PIPE_CHUNK")) {
         o.pipe_chunk = unset ? -1 : atoi(value) / 32 * 32;
+    } else if (!strcmp(key, "GRID_PIPE_WARPS")) {
+        o.pipe_warps = unset ? 0 : atoi(value);
     } else {
         return GRID_NS::fail_msg("grid_set_option: unknown key");
     }
@@ -87,11 +90,14 @@ int grid_set_option(const char *key, const char *value) {
 
 /* kernels launched: a call served by the phase-split kernels launches one kernel per stage */
 long long grid_launch_count(void) {
+    long long n = GRID_NS::g_launches.load();
 #ifdef GRID_HAS_PIPE
-    return GRID_NS::g_launches.load() + GRID_NS::pipe::g_kernel_launches.load() - GRID_NS::pipe::g_calls.load();
-#else
-    return GRID_NS::g_launches.load();
+    n += GRID_NS::pipe::g_kernel_launches.load() - GRID_NS::pipe::g_calls.load();
 #endif
+#ifdef GRID_HAS_LPS
+    n += GRID_NS::lps::g_kernel_launches.load() - GRID_NS::lps::g_calls.load();
+#endif
+    return n;
 }
 
 #define GRID_LAUNCH(expr, name)                                         \
@@ -286,8 +292,16 @@ static int run_pipelined(grid_data *hd, int T, const Span *ins, int n_ins, const
     GRID_CU(cudaGetDevice(&dev), "cudaGetDevice");
     if (dev != hd->device)
         return fail_msg("this grid_data was created on another device: cudaSetDevice() to it before calling");
+    // chunks: at most 2 per stream, at least kMinChunk states and ~kMinChunkBytes of traffic each - every
+    // cudaMemcpyAsync costs ~10 us of fixed DMA set-up, which 16 half-megabyte copies would not amortise
+    // (fused consumers move 140 B per iiwa14 state: 4 chunks beat 8 by 15 %, profiles/r2_*)
     int chunks = (T + kMinChunk - 1) / kMinChunk;
     if (chunks > 2 * kStreams) chunks = 2 * kStreams;
+    size_t words = 0;
+    for (int i = 0; i < n_ins; i++) words += ins[i].words;
+    for (int o = 0; o < n_outs; o++) words += outs[o].words;
+    const size_t by_bytes = (size_t)T * words * sizeof(float) / kMinChunkBytes;
+    if ((size_t)chunks > by_bytes) chunks = by_bytes < 1 ? 1 : (int)by_bytes;
     const int per = (T + chunks - 1) / chunks;
     // On the first failure: stop enqueueing, but still wait for every stream - copies that are already
     // in flight use the caller's buffers, which the caller is free to release once this returns.

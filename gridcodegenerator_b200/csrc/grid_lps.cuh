@@ -1,0 +1,603 @@
+// grid_lps.cuh - serial chains of any length: lane = state, ROLLED loops over the joints.
+//
+// The traced straight-line programs stop at ~20 k operations per thread; a 64-link chain's Minv or a single
+// gradient column is longer than that, and round 1 served such robots with the CTA-per-state kernels
+// (grid_wps.cuh): one CTA of 4-5 warps per SM, 176 KB of shared memory per state, 22.8 ms for the FD gradient
+// of 16 384 states of the 64-link chain (3.4 % of the FP32 roofline).  These kernels keep the decomposition
+// of the phase-split kernels - a per-state program followed by one program per du-column, 32 consecutive
+// states per warp - but write the programs as loops over the joint index with the joint's constants read from
+// constant memory (the index is warp-uniform), so the code is a few KB and stays in the instruction cache,
+// every lane works on its own state (no shuffles, no barriers inside a program), and a batch exposes
+// states x columns independent warps instead of states CTAs.
+//
+//   stage A (warp = 32 states): X_i(q), the composite base transforms, RNEA bias forces, the articulated-body
+//            inertia pass (U_i, Dinv_i), qdd by an O(n) articulated-body solve (no Minv needed), RNEA at qdd;
+//            per-joint results go to a scratch array [tile][joint][word][lane] (one 128-byte line per access).
+//   Minv columns (warp = 32 states x column j): the column recursions of reference algorithms/_direct_minv.py
+//            restricted to one column: backward j..0, forward 0..j.
+//   gradient columns (warp = 32 states x du-column): the forward recursion of reference
+//            algorithms/_inverse_dynamics_gradient.py:189-430 for one column.  The BACKWARD accumulation
+//            (:477-541) needs every df_i of the column again in reverse order (the wide kernel stores them:
+//            100 KB per state); here each df_i is moved to the BASE frame as soon as it exists
+//            (f0_i = (iX0)^T df_i), so the accumulated force at joint i is a suffix sum,
+//            dc_i = s0_i . (Total - sum_{k<i} f0_k), and one scalar per joint is all that is kept.
+//            For the FD gradient the column is then multiplied by -Minv WITHOUT Minv: an O(n)
+//            articulated-body solve with the U_i, Dinv_i of stage A replaces the n x n product of
+//            reference algorithms/_forward_dynamics_gradient.py:48-57 (4 n^3 flops per state, the only
+//            GEMM-shaped step of the path) - which is also this repo's answer to "tensor cores?" for chains.
+//
+// Needs, from the generated translation unit (GRID_NS::gen): struct WT (N) and the __constant__ tables wt_S,
+// wt_E0, wt_r0, wt_I, wt_damping (emit_wps_tables); and grid_wps.cuh for the spatial-algebra helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include "grid_wps.cuh"
+#define GRID_HAS_LPS 1
+
+namespace GRID_NS { namespace lps {
+
+using namespace gen;
+using wps::Xf;
+using wps::xmotion;
+using wps::xtforce;
+using wps::mxS;
+using wps::crossf;
+using wps::imul;
+using wps::pick;
+using wps::add_at;
+using wps::cross3;
+using wps::mat3T;
+
+constexpr int N = WT::N;
+constexpr int W = 64;                  // scratch words per joint and state
+// word offsets inside a joint's block
+constexpr int wE = 0, wR = 9;          // X_i(q): E (row-major 3x3), r
+constexpr int wV = 12, wIV = 18;       // v_i, I_i v_i
+constexpr int wMXA = 24, wMF = 30;     // mxS(X a_parent), mxS(f_i)   (wMF doubles as temporary f_i storage)
+constexpr int wE0 = 36, wR0 = 45;      // composite iX0: base -> joint i
+constexpr int wS0 = 48;                // joint axis in base coordinates (motion vector)
+constexpr int wU = 54, wDINV = 60;     // articulated-body U_i = IA_i S_i, 1 / (S_i^T U_i)
+constexpr int wQD = 61, wY = 62, wQDD = 63;
+constexpr int PITCH = 33;              // row pitch of the per-warp [joint][lane] staging tile
+
+static std::atomic<long long> g_kernel_launches{0};
+static std::atomic<long long> g_calls{0};
+
+__device__ __forceinline__ float *joint_ptr(float *tile_lane, int i) { return tile_lane + (size_t)i * (W * 32); }
+__device__ __forceinline__ void ld6(const float *p, float *o) {
+#pragma unroll
+    for (int r = 0; r < 6; r++) o[r] = p[32 * r];
+}
+__device__ __forceinline__ void st6(float *p, const float *o) {
+#pragma unroll
+    for (int r = 0; r < 6; r++) p[32 * r] = o[r];
+}
+__device__ __forceinline__ Xf ldX(const float *p) {       // p = joint block + wE (or wE0)
+    Xf x;
+#pragma unroll
+    for (int e = 0; e < 9; e++) x.E[e] = p[32 * e];
+#pragma unroll
+    for (int e = 0; e < 3; e++) x.r[e] = p[32 * (9 + e)];
+    return x;
+}
+__device__ __forceinline__ void stX(float *p, const Xf &x) {
+#pragma unroll
+    for (int e = 0; e < 9; e++) p[32 * e] = x.E[e];
+#pragma unroll
+    for (int e = 0; e < 3; e++) p[32 * (9 + e)] = x.r[e];
+}
+__device__ __forceinline__ float dot6(const float *a, const float *b) {
+    float s = a[0] * b[0];
+#pragma unroll
+    for (int r = 1; r < 6; r++) s = fmaf(a[r], b[r], s);
+    return s;
+}
+
+// X_i(q) = X_joint(q) X_tree as (E, r): the same update the wide kernels do (wps::update_X), per thread
+__device__ __forceinline__ Xf joint_X(int i, float q) {
+    const int k = wt_S[i];
+    const float *E0 = wt_E0 + 9 * i;
+    Xf X;
+#pragma unroll
+    for (int e = 0; e < 9; e++) X.E[e] = E0[e];
+    X.r[0] = wt_r0[3 * i]; X.r[1] = wt_r0[3 * i + 1]; X.r[2] = wt_r0[3 * i + 2];
+    if (k < 3) {
+        float sn, cs;
+        sincosf(q, &sn, &cs);
+        const int a = (k + 1) % 3, b = (k + 2) % 3;
+#pragma unroll
+        for (int col = 0; col < 3; col++) {
+            const float ea = E0[3 * a + col], eb = E0[3 * b + col];
+            const float na = cs * ea + sn * eb, nb = cs * eb - sn * ea;
+#pragma unroll
+            for (int row = 0; row < 3; row++) {
+                if (row == a) X.E[3 * row + col] = na;
+                if (row == b) X.E[3 * row + col] = nb;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 3; t++) X.r[t] += q * E0[3 * (k - 3) + t];
+    }
+    return X;
+}
+
+// IA <- X^T (IA - U Dinv U^T) X for a symmetric 6x6 (full storage), X = (E, r)
+__device__ __forceinline__ void abi_to_parent(const Xf &X, const float *IA, const float *U, float Dinv, float *out) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        float e[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, x[6], t[6], o[6];
+        e[c] = 1.0f;
+        xmotion(X, e, x);                              // column c of X
+        const float ux = dot6(U, x) * Dinv;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            float acc = -U[r] * ux;
+#pragma unroll
+            for (int cc = 0; cc < 6; cc++) acc = fmaf(IA[6 * r + cc], x[cc], acc);
+            t[r] = acc;
+        }
+        xtforce(X, t, o);
+#pragma unroll
+        for (int r = 0; r < 6; r++) out[6 * r + c] = o[r];
+    }
+}
+
+// ---- stage A ------------------------------------------------------------------------------------
+// FLAGS: bit 0 = bias forces c (RNEA at qdd = 0), bit 1 = articulated-body inertias (U, Dinv),
+//        bit 2 = qdd = FD(q, qd, u) (needs bits 0 and 1), bit 3 = qdd given in d_qdd,
+//        bit 4 = gradient exports (RNEA at qdd -> mxS(X a_parent), mxS(f)), bit 5 = write qdd to d_qdd_out
+template <int FLAGS>
+__global__ void __launch_bounds__(128)
+stage_a_kernel(const float *__restrict__ d_in, int stride, const float *__restrict__ d_qdd, float *__restrict__ scratch,
+               float *__restrict__ d_qdd_out, int num_states, float gravity) {
+    constexpr bool C0 = FLAGS & 1, ABI = FLAGS & 2, SOLVE = FLAGS & 4, QDD_IN = FLAGS & 8, GRAD = FLAGS & 16, QDD_OUT = FLAGS & 32;
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int ntiles = (num_states + 31) >> 5;
+    if (tile >= ntiles) return;
+    const long long st = min((long long)tile * 32 + lane, (long long)num_states - 1);   // ragged tile: recompute the last state
+    const bool valid = (long long)tile * 32 + lane < num_states;
+    const float *row = d_in + st * stride;
+    float *s = scratch + (size_t)tile * (N * W * 32) + lane;
+
+    // pass 1 (forward): X, composite base transform, joint axis in base coordinates, v, I v, f at qdd = 0
+    {
+        Xf Xc;
+        float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < N; i++) {
+            const int k = wt_S[i];
+            const float q = __ldg(row + i), qd = __ldg(row + N + i);
+            const Xf X = joint_X(i, q);
+            float *sj = joint_ptr(s, i);
+            stX(sj + 32 * wE, X);
+            if (i == 0) {
+                Xc = X;
+            } else {                                   // iX0 = X_i (i-1)X0: E = E_i E_c, r = r_c + E_c^T r_i
+                Xf Y;
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+                        Y.E[3 * r + c] = X.E[3 * r] * Xc.E[c] + X.E[3 * r + 1] * Xc.E[3 + c] + X.E[3 * r + 2] * Xc.E[6 + c];
+                float t[3];
+                mat3T(Xc.E, X.r, t);
+                Y.r[0] = Xc.r[0] + t[0]; Y.r[1] = Xc.r[1] + t[1]; Y.r[2] = Xc.r[2] + t[2];
+                Xc = Y;
+            }
+            stX(sj + 32 * wE0, Xc);
+            {   // s0 = 0X_i S_i: revolute [w ; r x w] with w = E_c^T e_k, prismatic [0 ; E_c^T e_k]
+                const int ax = k < 3 ? k : k - 3;
+                const float w[3] = {Xc.E[3 * ax], Xc.E[3 * ax + 1], Xc.E[3 * ax + 2]};
+                float s0[6], t[3];
+                cross3(Xc.r, w, t);
+                const bool rev = k < 3;
+                s0[0] = rev ? w[0] : 0.f; s0[1] = rev ? w[1] : 0.f; s0[2] = rev ? w[2] : 0.f;
+                s0[3] = rev ? t[0] : w[0]; s0[4] = rev ? t[1] : w[1]; s0[5] = rev ? t[2] : w[2];
+                st6(sj + 32 * wS0, s0);
+            }
+            float vn[6];
+            if (i == 0) {
+#pragma unroll
+                for (int r = 0; r < 6; r++) vn[r] = 0.f;
+            } else {
+                xmotion(X, v, vn);
+            }
+            add_at(vn, k, qd);
+            float iv[6];
+            imul(i, vn, iv);
+            st6(sj + 32 * wV, vn);
+            st6(sj + 32 * wIV, iv);
+            sj[32 * wQD] = qd;
+            if (C0) {
+                float an[6], t[6], f[6];
+                if (i == 0) {
+                    float e[6] = {0.f, 0.f, 0.f, 0.f, 0.f, gravity};
+                    xmotion(X, e, an);                 // X[:,5] * gravity (algorithms/_inverse_dynamics.py:123)
+                } else {
+                    xmotion(X, a, an);
+                    mxS(k, vn, t);
+#pragma unroll
+                    for (int r = 0; r < 6; r++) an[r] = fmaf(t[r], qd, an[r]);
+                }
+                imul(i, an, f);
+                crossf(vn, iv, t);
+#pragma unroll
+                for (int r = 0; r < 6; r++) { f[r] += t[r]; a[r] = an[r]; }
+                st6(sj + 32 * wMF, f);
+            }
+#pragma unroll
+            for (int r = 0; r < 6; r++) v[r] = vn[r];
+        }
+    }
+    // pass 2 (backward): c_i, articulated-body inertias, first half of the solve qdd = Minv (u - c)
+    if (C0 || ABI) {
+        float fc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Ft[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float IAc[36];
+#pragma unroll
+        for (int e = 0; e < 36; e++) IAc[e] = 0.f;
+        for (int i = N - 1; i >= 0; i--) {
+            const int k = wt_S[i];
+            float *sj = joint_ptr(s, i);
+            const Xf X = ldX(sj + 32 * wE);
+            float c = 0.f;
+            if (C0) {
+                float f[6];
+                ld6(sj + 32 * wMF, f);
+#pragma unroll
+                for (int r = 0; r < 6; r++) f[r] += fc[r];
+                c = pick(f, k) + wt_damping[i] * sj[32 * wQD];
+                xtforce(X, f, fc);
+            }
+            if (ABI) {
+                float IA[36], U[6];
+#pragma unroll
+                for (int e = 0; e < 36; e++) IA[e] = wt_I[36 * i + e] + IAc[e];
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    float u = IA[6 * r];
+#pragma unroll
+                    for (int t = 1; t < 6; t++) u = (k == t) ? IA[6 * r + t] : u;
+                    U[r] = u;
+                }
+                const float Dinv = 1.0f / pick(U, k);
+                st6(sj + 32 * wU, U);
+                sj[32 * wDINV] = Dinv;
+                if (SOLVE) {
+                    const float tau = __ldg(row + 2 * N + i) - c;
+                    const float y = Dinv * (tau - pick(Ft, k));
+                    sj[32 * wY] = y;
+                    float t[6];
+#pragma unroll
+                    for (int r = 0; r < 6; r++) t[r] = fmaf(U[r], y, Ft[r]);
+                    xtforce(X, t, Ft);
+                }
+                if (i > 0) abi_to_parent(X, IA, U, Dinv, IAc);
+            }
+        }
+    }
+    // pass 3 (forward): second half of the solve
+    if (SOLVE) {
+        float ap[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < N; i++) {
+            const int k = wt_S[i];
+            float *sj = joint_ptr(s, i);
+            float U[6], t[6];
+            ld6(sj + 32 * wU, U);
+            if (i > 0) {
+                const Xf X = ldX(sj + 32 * wE);
+                xmotion(X, ap, t);
+#pragma unroll
+                for (int r = 0; r < 6; r++) ap[r] = t[r];
+            }
+            const float qdd = sj[32 * wY] - sj[32 * wDINV] * dot6(U, ap);
+            add_at(ap, k, qdd);
+            sj[32 * wQDD] = qdd;
+            if (QDD_OUT && valid) d_qdd_out[st * N + i] = qdd;
+        }
+    }
+    // pass 4: RNEA at qdd -> mxS(X a_parent) and mxS(f)
+    if (GRAD) {
+        float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < N; i++) {
+            const int k = wt_S[i];
+            float *sj = joint_ptr(s, i);
+            const Xf X = ldX(sj + 32 * wE);
+            float v[6], iv[6], Xa[6], t[6], f[6];
+            ld6(sj + 32 * wV, v);
+            ld6(sj + 32 * wIV, iv);
+            const float qd = sj[32 * wQD];
+            const float qdd = QDD_IN ? __ldg(d_qdd + st * N + i) : (SOLVE ? sj[32 * wQDD] : 0.f);
+            if (i == 0) {
+                float e[6] = {0.f, 0.f, 0.f, 0.f, 0.f, gravity};
+                xmotion(X, e, Xa);
+            } else {
+                xmotion(X, a, Xa);
+            }
+            mxS(k, Xa, t);
+            st6(sj + 32 * wMXA, t);
+#pragma unroll
+            for (int r = 0; r < 6; r++) a[r] = Xa[r];
+            add_at(a, k, qdd);
+            if (i > 0) {
+                mxS(k, v, t);
+#pragma unroll
+                for (int r = 0; r < 6; r++) a[r] = fmaf(t[r], qd, a[r]);
+            }
+            imul(i, a, f);
+            crossf(v, iv, t);
+#pragma unroll
+            for (int r = 0; r < 6; r++) f[r] += t[r];
+            st6(sj + 32 * wMF, f);
+        }
+        float fc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = N - 1; i >= 0; i--) {
+            const int k = wt_S[i];
+            float *sj = joint_ptr(s, i);
+            float f[6], t[6];
+            ld6(sj + 32 * wMF, f);
+#pragma unroll
+            for (int r = 0; r < 6; r++) f[r] += fc[r];
+            mxS(k, f, t);
+            st6(sj + 32 * wMF, t);
+            if (i > 0) {
+                const Xf X = ldX(sj + 32 * wE);
+                xtforce(X, f, fc);
+            }
+        }
+    }
+}
+
+// per-warp [joint][lane] tile -> LEN contiguous words per state at g_tile + state * out_words + off
+__device__ __forceinline__ void store_rows(float *__restrict__ g_tile, long long out_words, int off, const float *sa,
+                                           int len, int cnt, int lane) {
+    __syncwarp();
+    for (int st = 0; st < cnt; st++)
+        for (int i = lane; i < len; i += 32) g_tile[(long long)st * out_words + off + i] = sa[i * PITCH + st];
+    __syncwarp();
+}
+
+// ---- Minv columns: warp = (32 states, column j) -----------------------------------------------------
+// replaces direct_minv_inner (algorithms/_direct_minv.py:23-382) for one column: F column backward from joint j
+// to the root, then forward from the root to j; rows below the diagonal are written as zeros.
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
+minv_columns_kernel(float *__restrict__ d_Minv, const float *__restrict__ scratch, int num_states, int ntiles) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *sa = smem + warp * (N * PITCH);
+    const long long task = (long long)blockIdx.x * WARPS + warp;       // column-major: long columns (large j) first
+    if (task >= (long long)N * ntiles) return;
+    const int j = N - 1 - (int)(task / ntiles), tile = (int)(task % ntiles);
+    const int cnt = min(32, num_states - tile * 32);
+    const float *s = scratch + (size_t)tile * (N * W * 32) + lane;
+    float F[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = j; i >= 0; i--) {
+        const int k = wt_S[i];
+        const float *sj = s + (size_t)i * (W * 32);
+        const float Dinv = sj[32 * wDINV];
+        const float m = (i == j ? Dinv : 0.f) - Dinv * pick(F, k);
+        sa[i * PITCH + lane] = m;
+        if (i > 0) {
+            float U[6], t[6];
+            ld6(sj + 32 * wU, U);
+#pragma unroll
+            for (int r = 0; r < 6; r++) t[r] = fmaf(U[r], m, F[r]);
+            const Xf X = ldX(sj + 32 * wE);
+            xtforce(X, t, F);
+        }
+    }
+    float G[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i <= j; i++) {
+        const int k = wt_S[i];
+        const float *sj = s + (size_t)i * (W * 32);
+        float m = sa[i * PITCH + lane];
+        if (i > 0) {
+            float U[6], t[6];
+            ld6(sj + 32 * wU, U);
+            const Xf X = ldX(sj + 32 * wE);
+            xmotion(X, G, t);
+#pragma unroll
+            for (int r = 0; r < 6; r++) G[r] = t[r];
+            m -= sj[32 * wDINV] * dot6(U, G);
+            sa[i * PITCH + lane] = m;
+        }
+        add_at(G, k, m);
+    }
+    for (int i = j + 1; i < N; i++) sa[i * PITCH + lane] = 0.f;
+    store_rows(d_Minv + (long long)tile * 32 * N * N, (long long)N * N, j * N, sa, N, cnt, lane);
+}
+
+// ---- gradient columns: warp = (32 states, du-column) ---------------------------------------------------
+// SOLVE = false: dc_du column; true: df_du column = -Minv dc_du column through the articulated-body solve.
+template <int WARPS, bool SOLVE>
+__global__ void __launch_bounds__(32 * WARPS)
+grad_columns_kernel(float *__restrict__ d_out, const float *__restrict__ scratch, int num_states, int ntiles) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *sa = smem + warp * (N * PITCH);
+    // task order: joint-major, the two sides of a joint adjacent, long columns (small j) first; the WARPS warps
+    // of a CTA take adjacent columns of ONE tile, so they read the same scratch lines at about the same time
+    const long long blk = blockIdx.x;
+    const int cgroups = (2 * N + WARPS - 1) / WARPS;
+    const int tile = (int)(blk % ntiles), cg = (int)(blk / ntiles);
+    const int cc = cg * WARPS + warp;
+    if (cg >= cgroups || cc >= 2 * N) return;
+    const int j = cc >> 1, side = cc & 1;
+    const int cnt = min(32, num_states - tile * 32);
+    const float *s = scratch + (size_t)tile * (N * W * 32) + lane;
+
+    float dv[6], da[6], P[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = j; i < N; i++) {
+        const int k = wt_S[i];
+        const float *sj = s + (size_t)i * (W * 32);
+        float v[6], iv[6], t[6];
+        ld6(sj + 32 * wV, v);
+        ld6(sj + 32 * wIV, iv);
+        const float qd = sj[32 * wQD];
+        if (i == j) {
+            if (side == 0) {
+                mxS(k, v, dv);                          // == mxS(X v_parent)
+                float mxa[6];
+                ld6(sj + 32 * wMXA, mxa);
+                mxS(k, dv, t);
+#pragma unroll
+                for (int r = 0; r < 6; r++) da[r] = fmaf(t[r], qd, mxa[r]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 6; r++) dv[r] = 0.f;
+                add_at(dv, k, 1.0f);
+                mxS(k, v, da);
+            }
+        } else {
+            const Xf X = ldX(sj + 32 * wE);
+            float n6[6];
+            xmotion(X, dv, n6);
+#pragma unroll
+            for (int r = 0; r < 6; r++) dv[r] = n6[r];
+            xmotion(X, da, n6);
+            mxS(k, dv, t);
+#pragma unroll
+            for (int r = 0; r < 6; r++) da[r] = fmaf(t[r], qd, n6[r]);
+        }
+        // df = I da + dv x* (I v) + v x* (I dv)
+        float df[6], idv[6];
+        imul(i, da, df);
+        crossf(dv, iv, t);
+#pragma unroll
+        for (int r = 0; r < 6; r++) df[r] += t[r];
+        imul(i, dv, idv);
+        crossf(v, idv, t);
+#pragma unroll
+        for (int r = 0; r < 6; r++) df[r] += t[r];
+        // base-frame bookkeeping: keep s0_i . (forces of the joints before i), add this joint's force
+        float s0[6];
+        ld6(sj + 32 * wS0, s0);
+        sa[i * PITCH + lane] = dot6(s0, P);
+        const Xf X0 = ldX(sj + 32 * wE0);
+        xtforce(X0, df, t);
+#pragma unroll
+        for (int r = 0; r < 6; r++) P[r] += t[r];
+    }
+    // rows: i >= j: s0_i . (Total - prefix_i); i < j: s0_i . (Total - [dq] mxS(f_j) in the base frame)
+    float T2[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) T2[r] = P[r];
+    if (side == 0) {
+        const float *sj = s + (size_t)j * (W * 32);
+        float mf[6], t[6];
+        ld6(sj + 32 * wMF, mf);
+        const Xf X0 = ldX(sj + 32 * wE0);
+        xtforce(X0, mf, t);
+#pragma unroll
+        for (int r = 0; r < 6; r++) T2[r] -= t[r];
+    }
+    for (int i = 0; i < N; i++) {
+        const float *sj = s + (size_t)i * (W * 32);
+        float s0[6];
+        ld6(sj + 32 * wS0, s0);
+        float dc = i < j ? dot6(s0, T2) : dot6(s0, P) - sa[i * PITCH + lane];
+        if (side == 1 && i == j) dc += wt_damping[i];
+        sa[i * PITCH + lane] = dc;
+    }
+    if (SOLVE) {
+        // x = Minv dc through the articulated-body recursions, then the column is -x
+        float F[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = N - 1; i >= 0; i--) {
+            const int k = wt_S[i];
+            const float *sj = s + (size_t)i * (W * 32);
+            const float y = sj[32 * wDINV] * (sa[i * PITCH + lane] - pick(F, k));
+            sa[i * PITCH + lane] = y;
+            if (i > 0) {
+                float U[6], t[6];
+                ld6(sj + 32 * wU, U);
+#pragma unroll
+                for (int r = 0; r < 6; r++) t[r] = fmaf(U[r], y, F[r]);
+                const Xf X = ldX(sj + 32 * wE);
+                xtforce(X, t, F);
+            }
+        }
+        float ap[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < N; i++) {
+            const int k = wt_S[i];
+            const float *sj = s + (size_t)i * (W * 32);
+            float x = sa[i * PITCH + lane];
+            if (i > 0) {
+                float U[6], t[6];
+                ld6(sj + 32 * wU, U);
+                const Xf X = ldX(sj + 32 * wE);
+                xmotion(X, ap, t);
+#pragma unroll
+                for (int r = 0; r < 6; r++) ap[r] = t[r];
+                x -= sj[32 * wDINV] * dot6(U, ap);
+            }
+            add_at(ap, k, x);
+            sa[i * PITCH + lane] = -x;
+        }
+    }
+    store_rows(d_out + (long long)tile * 32 * 2 * N * N, (long long)2 * N * N, side * N * N + j * N, sa, N, cnt, lane);
+}
+
+// ---- launchers -------------------------------------------------------------------------------------------
+constexpr int kColWarps = 8;
+constexpr int kChunkStates = 4096;     // scratch of a chunk: 4096 x N x 256 B (64-link chain: 67 MB, about half of L2)
+
+template <class K>
+static cudaError_t opt_in_smem(K kern, size_t bytes) {
+    static bool done[kMaxDevices];
+    int dev = 0;
+    if (cudaError_t e = current_device(dev)) return e;
+    if (!done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        done[dev] = true;
+    }
+    return cudaSuccess;
+}
+
+// ALG: 0 = Minv, 1 = FD, 2 = ID gradient (HAS_QDD: qdd given), 3 = FD gradient
+template <int ALG, bool HAS_QDD>
+cudaError_t lps_launch(float *d_out, const float *d_in, int stride, const float *d_qdd, int num_states, float gravity,
+                       cudaStream_t stream) {
+    if (num_states <= 0) return cudaSuccess;
+    g_calls.fetch_add(1);
+    constexpr int FLAGS = ALG == 0 ? 2 : ALG == 1 ? (1 | 2 | 4 | 32) : ALG == 2 ? (16 | (HAS_QDD ? 8 : 0)) : (1 | 2 | 4 | 16);
+    constexpr size_t col_smem = sizeof(float) * N * PITCH * kColWarps;
+    cudaError_t e = cudaSuccess;
+    if (ALG == 0) e = opt_in_smem(minv_columns_kernel<kColWarps>, col_smem);
+    if (ALG == 2) e = opt_in_smem(grad_columns_kernel<kColWarps, false>, col_smem);
+    if (ALG == 3) e = opt_in_smem(grad_columns_kernel<kColWarps, true>, col_smem);
+    if (e != cudaSuccess) return e;
+    const int chunk = num_states < kChunkStates ? num_states : kChunkStates;
+    const size_t sc_bytes = (size_t)((chunk + 31) / 32) * N * W * 32 * sizeof(float);
+    float *scratch = nullptr;
+    keep_pool_memory();
+    e = cudaMallocAsync((void **)&scratch, sc_bytes, stream);
+    if (e != cudaSuccess) return e;
+    for (int first = 0; first < num_states && e == cudaSuccess; first += chunk) {
+        const int n = num_states - first < chunk ? num_states - first : chunk;
+        const int ntiles = (n + 31) / 32;
+        const float *in = d_in + (long long)first * stride;
+        const float *qdd = d_qdd ? d_qdd + (long long)first * N : nullptr;
+        stage_a_kernel<FLAGS><<<(ntiles + 3) / 4, 128, 0, stream>>>(in, stride, qdd, scratch,
+                                                                    ALG == 1 ? d_out + (long long)first * N : nullptr, n, gravity);
+        g_kernel_launches.fetch_add(1);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if (ALG == 0) {
+            const long long tasks = (long long)N * ntiles;
+            minv_columns_kernel<kColWarps><<<(unsigned)((tasks + kColWarps - 1) / kColWarps), 32 * kColWarps, col_smem, stream>>>(
+                d_out + (long long)first * N * N, scratch, n, ntiles);
+            g_kernel_launches.fetch_add(1);
+        } else if (ALG >= 2) {
+            const long long blocks = (long long)((2 * N + kColWarps - 1) / kColWarps) * ntiles;
+            auto kern = ALG == 3 ? grad_columns_kernel<kColWarps, true> : grad_columns_kernel<kColWarps, false>;
+            kern<<<(unsigned)blocks, 32 * kColWarps, col_smem, stream>>>(d_out + (long long)first * 2 * N * N, scratch, n, ntiles);
+            g_kernel_launches.fetch_add(1);
+        }
+        e = cudaGetLastError();
+    }
+    cudaError_t e2 = cudaFreeAsync(scratch, stream);
+    return e != cudaSuccess ? e : e2;
+}
+
+}}  // namespace GRID_NS::lps

@@ -234,6 +234,10 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
         const long long items_w = (long long)ntasks * ((ntiles + opt_w[i] - 1) / opt_w[i]);
         if (items_w >= 2LL * sms * per_sm[i]) break;
     }
+    if (const int forced = options().pipe_warps) {        // experiments: GRID_PIPE_WARPS pins the CTA width
+        for (int i = 0; i < NOPT; i++)
+            if (opt_w[i] == forced && per_sm[i] >= 1) wi = i;
+    }
     if (wi < 0) return cudaErrorLaunchOutOfResources;
     const int w = opt_w[wi];
     const int nblk = (ntiles + w - 1) / w;
@@ -259,23 +263,6 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
 // of their component on a per-(task, tile) flag (release/acquire at gpu scope).  Dependencies only
 // point to lower CTA indices, which the hardware schedules first, so the kernel cannot deadlock
 // even when not all CTAs are resident at once.
-// The scratch array comes from the stream-ordered allocator (no library state, safe with concurrent
-// callers on different streams); keeping the pool's memory between calls makes the allocation a
-// free-list hit after the first launch.
-static void keep_pool_memory() {
-    static bool dones[kMaxDevices];
-    int dev = 0;
-    if (current_device(dev) != cudaSuccess) return;
-    bool &done = dones[dev];
-    if (done) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    done = true;
-}
-
 struct PipePart {
     short first[64], count[64];
 };

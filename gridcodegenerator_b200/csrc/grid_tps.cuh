@@ -17,11 +17,12 @@ namespace GRID_NS {
 // ---- process-wide options --------------------------------------------------------------------
 // Read from the environment ONCE (first use), changed afterwards only through grid_set_option()
 // (include/grid_b200.h): the launch path never calls getenv.
-enum ForceKernel { kAuto = 0, kTps = 1, kWps = 2, kCps = 3, kPipe = 4 };
+enum ForceKernel { kAuto = 0, kTps = 1, kWps = 2, kCps = 3, kPipe = 4, kLps = 5 };
 struct Options {
     int force_kernel;       // ForceKernel
     int pipe_fused;         // 1 = experimental single-launch variant of the phase-split kernels
     int pipe_chunk;         // states per chunk of a two-stage launch; -1 = the compiled default
+    int pipe_warps;         // warps per CTA of the phase-split kernels; 0 = chosen from the batch size
 };
 inline int parse_force(const char *f) {
     if (!f || !*f) return kAuto;
@@ -29,6 +30,7 @@ inline int parse_force(const char *f) {
     if (!strcmp(f, "wps")) return kWps;
     if (!strcmp(f, "cps")) return kCps;
     if (!strcmp(f, "pipe")) return kPipe;
+    if (!strcmp(f, "lps")) return kLps;
     return -1;
 }
 inline Options &options() {
@@ -40,6 +42,8 @@ inline Options &options() {
         x.pipe_fused = (m && !strcmp(m, "fused")) ? 1 : 0;
         const char *c = getenv("GRID_PIPE_CHUNK");
         x.pipe_chunk = c ? atoi(c) / 32 * 32 : -1;
+        const char *w = getenv("GRID_PIPE_WARPS");
+        x.pipe_warps = w ? atoi(w) : 0;
         return x;
     }();
     return o;
@@ -54,6 +58,23 @@ inline cudaError_t current_device(int &dev) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     return (dev < 0 || dev >= kMaxDevices) ? cudaErrorInvalidDevice : cudaSuccess;
+}
+
+// The scratch arrays of the phase-split and chain kernels come from the stream-ordered allocator (no library
+// state, safe with concurrent callers on different streams); keeping the pool's memory between calls makes the
+// allocation a free-list hit after the first launch.
+static void keep_pool_memory() {
+    static bool dones[kMaxDevices];
+    int dev = 0;
+    if (current_device(dev) != cudaSuccess) return;
+    bool &done = dones[dev];
+    if (done) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done = true;
 }
 
 constexpr int odd_pad(int words) { return words | 1; }   // odd stride => conflict-free lane access

@@ -512,6 +512,71 @@ __device__ void grad_column(float *s, int ct, bool valid) {
     }
 }
 
+// ---- df_du = -Minv dc_du on the tensor cores (3xTF32), measured variant ----------------------------
+// BASELINE.json north_star: "tensor cores only if a batched product in the gradient path measurably wins at
+// the stated tolerance".  The product is (N x N) (N x 2N) per state.  mma.sync.m16n8k8 TF32 with the 3xTF32
+// split (hi*hi + hi*lo + lo*hi) keeps FP32-class accuracy (1.4e-6 relative at N = 64, 5e-4 for one TF32
+// pass - too close to the 1e-3 bar; profiles/r2_micro_tc_minv_gemm.jsonl).  Operands are first copied into
+// row-padded staging (pitch N + 4: conflict-free fragment loads) in the df/sv region, which is dead once
+// grad_column has run.  Warp w < N/16 owns rows [16w, 16w + 16).  Selected by WT::TC_MATMUL
+// (KernelPlan(wps_tc_matmul=True)); needs N % 16 == 0.
+__device__ __forceinline__ unsigned to_tf32(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <int NN>
+__device__ __forceinline__ void matmul_tc3(float *s) {
+    constexpr int P = NN + 4, MT = NN / 16, NTL = 2 * NN / 8;
+    static_assert(NN % 16 == 0, "tensor-core product needs N % 16 == 0");
+    static_assert(3 * NN * P <= 2 * WT::DF_WORDS + WT::NSAVE * 12 * 2 * NN, "staging does not fit the dead df/sv region");
+    static_assert(MT * 32 <= NT, "not enough warps");
+    float *pA = s + L::df, *pB = pA + NN * P;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    for (int e = tid; e < NN * NN; e += NT) pA[(e / NN) * P + e % NN] = s[L::Minv + e];
+    for (int e = tid; e < 2 * NN * NN; e += NT) pB[(e / NN) * P + e % NN] = s[L::dc + e];
+    __syncthreads();
+    if (warp < MT) {
+        float acc[NTL][4];
+#pragma unroll
+        for (int j = 0; j < NTL; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+        for (int k0 = 0; k0 < NN; k0 += 8) {
+            const float af[4] = {pA[(16 * warp + g) * P + k0 + t], pA[(16 * warp + g + 8) * P + k0 + t],
+                                 pA[(16 * warp + g) * P + k0 + t + 4], pA[(16 * warp + g + 8) * P + k0 + t + 4]};
+            unsigned ah[4], al[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                ah[i] = to_tf32(af[i]);
+                al[i] = to_tf32(af[i] - __uint_as_float(ah[i]));
+            }
+#pragma unroll
+            for (int j = 0; j < NTL; j++) {
+                const float bf[2] = {pB[(8 * j + g) * P + k0 + t], pB[(8 * j + g) * P + k0 + t + 4]};
+                const unsigned bh[2] = {to_tf32(bf[0]), to_tf32(bf[1])};
+                const unsigned bl[2] = {to_tf32(bf[0] - __uint_as_float(bh[0])), to_tf32(bf[1] - __uint_as_float(bh[1]))};
+                mma_m16n8k8_tf32(acc[j], al, bh);                // small terms first
+                mma_m16n8k8_tf32(acc[j], ah, bl);
+                mma_m16n8k8_tf32(acc[j], ah, bh);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NTL; j++) {
+            const int c0 = 8 * j + 2 * t, r0 = 16 * warp + g;
+            s[L::dc + c0 * NN + r0] = -acc[j][0];
+            s[L::dc + (c0 + 1) * NN + r0] = -acc[j][1];
+            s[L::dc + c0 * NN + r0 + 8] = -acc[j][2];
+            s[L::dc + (c0 + 1) * NN + r0 + 8] = -acc[j][3];
+        }
+    }
+    __syncthreads();
+}
+
 // ALG: 0 = Minv, 1 = FD, 2 = ID gradient, 3 = FD gradient.
 // EXTRA: ALG 2 -> qdd given (USE_QDD_FLAG); ALG 3 -> qdd and Minv given (USE_QDD_MINV_FLAG).
 //
@@ -564,7 +629,9 @@ __device__ __forceinline__ void wps_compute(float *s, float gravity) {
         if (tid < WT::COL_WARPS * 32)            // whole warps: grad_column votes with a full mask
             grad_column(s, tid < 2 * N ? tid : 2 * N - 1, tid < 2 * N);
         __syncthreads();
-        if (ALG == 3) {
+        if constexpr (ALG == 3 && WT::TC_MATMUL && N % 16 == 0) {
+            matmul_tc3<N>(s);
+        } else if (ALG == 3) {
             // df_du[:, col] = -Minv dc_du[:, col]  (algorithms/_forward_dynamics_gradient.py:48-57)
             // each lane owns one column: read it into registers, overwrite it in place
             for (int col = tid; col < 2 * N; col += NT) {
@@ -666,6 +733,48 @@ __device__ __forceinline__ void wps_inner(float *s_out, const float *s_q, const 
     } else {
         for (int e = tid; e < 2 * N * N; e += NT) s_out[e] = s[L::dc + e];
     }
+    __syncthreads();
+}
+
+// inverse_dynamics_gradient_inner of the reference takes the RNEA results (v, a, f of every joint,
+// s_vaf = [v(6n) | a(6n) | f(6n)]) instead of computing them (algorithms/_inverse_dynamics_gradient.py:
+// 27-41).  X a_parent is recovered from a_i: mxS(X a_p) = mxS(a_i - mxS(v_i) qd_i) because mxS_k(e_k) = 0.
+__device__ __forceinline__ void wps_grad_inner_vaf(float *s_out, const float *s_q, const float *s_qd,
+                                                   const float *s_vaf, float *s_work) {
+    float *s = s_work;
+    const int tid = threadIdx.x;
+    __syncthreads();
+    for (int e = tid; e < 36 * N; e += NT) s[L::Ic + e] = __ldg(wt_I_g + e);
+    for (int e = tid; e < N; e += NT) { s[L::q + e] = s_q[e]; s[L::qd + e] = s_qd[e]; }
+    for (int e = tid; e < 6 * N; e += NT) { s[L::v + e] = s_vaf[e]; s[L::f + e] = s_vaf[12 * N + e]; }
+    __syncthreads();
+    for (int i = tid; i < N; i += NT) {
+        update_X(s, i);
+        const int k = wt_S[i];
+        float v6[6], a6[6], t[6], iv[6];
+        load6(s + L::v + 6 * i, v6);
+        load6(s_vaf + 6 * N + 6 * i, a6);
+        if (wt_parent[i] >= 0) {
+            mxS(k, v6, t);
+            const float qdi = s[L::qd + i];
+#pragma unroll
+            for (int r = 0; r < 6; r++) a6[r] -= t[r] * qdi;
+        }
+        store6(s + L::Xa + 6 * i, a6);
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 6; c++) acc = fmaf(s[L::Ic + 36 * i + 6 * r + c], v6[c], acc);
+            iv[r] = acc;
+        }
+        store6(s + L::Iv + 6 * i, iv);
+    }
+    for (int e = tid; e < 2 * N * N; e += NT) s[L::dc + e] = 0.f;
+    __syncthreads();
+    if (tid < WT::COL_WARPS * 32) grad_column(s, tid < 2 * N ? tid : 2 * N - 1, tid < 2 * N);
+    __syncthreads();
+    for (int e = tid; e < 2 * N * N; e += NT) s_out[e] = s[L::dc + e];
     __syncthreads();
 }
 

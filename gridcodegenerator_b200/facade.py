@@ -754,6 +754,29 @@ class GRiDCodeGenerator:
             return True
         return False
 
+    def _wide(self, alg_key):
+        """True when the _inner/_device functions of this algorithm are served by the wide CTA-per-state body
+        (csrc/grid_wps.cuh wps_inner): robots whose single-thread program is too large (Atlas, 64-link chain)."""
+        return self._family[alg_key] == "wps"
+
+    def _wide_temp_words(self):
+        return self._plan.wps["smem_bytes"] // 4
+
+    def _wide_fn(self, doc, signature, call, device=False):
+        """Reference-signature wrapper around a wide body.  `call` is the wps function call with `S_WORK` standing
+        for the scratch block: the caller's s_temp (_inner) or this block's dynamic shared memory (_device)."""
+        notes = ["all threads of the block must call; blockDim.x must be SUGGESTED_THREADS (%d)" % self._plan.wps["NT"],
+                 ("uses %d floats of dynamic shared memory (launch the calling kernel with that much)"
+                  if device else "s_temp: %d floats, 16-byte aligned") % self._wide_temp_words()]
+        self.gen_add_func_doc(doc, notes, [], None)
+        self.gen_add_code_lines(["template <typename T>", "__device__", signature])
+        self.code_str += "    static_assert(std::is_same<T,float>::value, \"T must be float\");\n"
+        if device:
+            self.code_str += "    extern __shared__ float4 s_wide_dyn4_[]; float *s_work_ = reinterpret_cast<float *>(s_wide_dyn4_);\n"
+        else:
+            self.code_str += "    float *s_work_ = s_temp;\n"
+        self.code_str += "    %s::wps::%s;\n}\n\n" % (self._impl_ns, call.replace("S_WORK", "s_work_"))
+
     # -- inverse dynamics
     def gen_inverse_dynamics_inner_temp_mem_size(self):
         return 0
@@ -936,7 +959,7 @@ class GRiDCodeGenerator:
 
     # -- direct minv
     def gen_direct_minv_inner_temp_mem_size(self):
-        return 0
+        return self._wide_temp_words() if self._wide("minv") else 0
 
     def gen_direct_minv_inner_function_call(self, use_thread_group=False, updated_var_names=None):
         v = dict(s_Minv_name="s_Minv", s_q_name="s_q", s_temp_name="s_temp")
@@ -945,6 +968,11 @@ class GRiDCodeGenerator:
                                                                                  v["s_temp_name"]))
 
     def gen_direct_minv_inner(self, use_thread_group=False):
+        if self._wide("minv"):
+            self._wide_fn("Compute the inverse of the mass matrix (upper triangle, column-major)",
+                          "void direct_minv_inner(T *s_Minv, const T *s_q, T *s_XImats, T *s_temp) {",
+                          "wps_inner<0, false>(s_Minv, s_q, nullptr, nullptr, nullptr, S_WORK, 0.f)")
+            return
         if self._too_large("minv", "direct_minv_inner"):
             return
         self._serial_device_fn("Compute the inverse of the mass matrix (upper triangle, column-major)",
@@ -952,6 +980,11 @@ class GRiDCodeGenerator:
                                A.trace_minv(self.robot), self._smem_in({"q": "s_q"}), lambda a, i: "s_Minv[%d]" % i)
 
     def gen_direct_minv_device(self, use_thread_group=False):
+        if self._wide("minv"):
+            self._wide_fn("Compute the inverse of the mass matrix (upper triangle, column-major)",
+                          "void direct_minv_device(T *s_Minv, const T *s_q, const robotModel<T> *d_robotModel){",
+                          "wps_inner<0, false>(s_Minv, s_q, nullptr, nullptr, nullptr, S_WORK, 0.f)", device=True)
+            return
         if self._too_large("minv", "direct_minv_device"):
             return
         self._serial_device_fn("Compute the inverse of the mass matrix (upper triangle, column-major)",
@@ -981,7 +1014,7 @@ class GRiDCodeGenerator:
 
     # -- forward dynamics
     def gen_forward_dynamics_inner_temp_mem_size(self):
-        return 0
+        return self._wide_temp_words() if self._wide("fd") else 0
 
     def gen_forward_dynamics_finish_function_call(self, updated_var_names=None):
         v = dict(s_qdd_name="s_qdd", s_u_name="s_u", s_c_name="s_c", s_Minv_name="s_Minv")
@@ -1003,6 +1036,12 @@ class GRiDCodeGenerator:
             v["s_qdd_name"], v["s_q_name"], v["s_qd_name"], v["s_u_name"], v["s_temp_name"], v["gravity_name"]))
 
     def gen_forward_dynamics_inner(self, use_thread_group=False):
+        if self._wide("fd"):
+            self._wide_fn("Computes forward dynamics",
+                          "void forward_dynamics_inner(T *s_qdd, const T *s_q, const T *s_qd, const T *s_u, "
+                          "T *s_XImats, T *s_temp, const T gravity) {",
+                          "wps_inner<1, false>(s_qdd, s_q, s_qd, s_u, nullptr, S_WORK, gravity)")
+            return
         if self._too_large("fd", "forward_dynamics_inner"):
             return
         self._serial_device_fn("Computes forward dynamics",
@@ -1011,6 +1050,12 @@ class GRiDCodeGenerator:
                                self._smem_in({"q": "s_q", "qd": "s_qd", "u": "s_u"}), lambda a, i: "s_qdd[%d]" % i)
 
     def gen_forward_dynamics_device(self, use_thread_group=False):
+        if self._wide("fd"):
+            self._wide_fn("Computes forward dynamics",
+                          "void forward_dynamics_device(T *s_qdd, const T *s_q, const T *s_qd, const T *s_u, "
+                          "const robotModel<T> *d_robotModel, const T gravity) {",
+                          "wps_inner<1, false>(s_qdd, s_q, s_qd, s_u, nullptr, S_WORK, gravity)", device=True)
+            return
         if self._too_large("fd", "forward_dynamics_device"):
             return
         self._serial_device_fn("Computes forward dynamics",
@@ -1039,10 +1084,10 @@ class GRiDCodeGenerator:
 
     # -- inverse dynamics gradient
     def gen_inverse_dynamics_gradient_inner_temp_mem_size(self):
-        return 0
+        return self._wide_temp_words() if self._wide("id_grad") else 0
 
     def gen_inverse_dynamics_gradient_kernel_max_temp_mem_size(self):
-        return 0
+        return self._wide_temp_words() if self._wide("id_grad") else 0
 
     def gen_inverse_dynamics_gradient_inner_function_call(self, use_thread_group=False, updated_var_names=None):
         v = dict(s_dc_du_name="s_dc_du", s_q_name="s_q", s_qd_name="s_qd", s_vaf_name="s_vaf", s_temp_name="s_temp",
@@ -1052,6 +1097,12 @@ class GRiDCodeGenerator:
             v["s_dc_du_name"], v["s_q_name"], v["s_qd_name"], v["s_vaf_name"], v["s_temp_name"], v["gravity_name"]))
 
     def gen_inverse_dynamics_gradient_inner(self, use_thread_group=False):
+        if self._wide("id_grad"):
+            self._wide_fn("Computes the gradient of inverse dynamics from v, a, f",
+                          "void inverse_dynamics_gradient_inner(T *s_dc_du, const T *s_q, const T *s_qd, "
+                          "const T *s_vaf, T *s_XImats, T *s_temp, const T gravity) {",
+                          "wps_grad_inner_vaf(s_dc_du, s_q, s_qd, s_vaf, S_WORK)")
+            return
         if self._too_large("id_grad", "inverse_dynamics_gradient_inner"):
             return
         self._serial_device_fn("Computes the gradient of inverse dynamics from v, a, f",
@@ -1062,6 +1113,14 @@ class GRiDCodeGenerator:
                                lambda a, i: "s_dc_du[%d]" % i)
 
     def gen_inverse_dynamics_gradient_device(self, use_thread_group=False, use_qdd_input=False):
+        if self._wide("id_grad"):
+            self._wide_fn("Computes the gradient of inverse dynamics",
+                          "void inverse_dynamics_gradient_device(T *s_dc_du, const T *s_q, const T *s_qd, %s"
+                          "const robotModel<T> *d_robotModel, const T gravity) {" % (
+                              "const T *s_qdd, " if use_qdd_input else ""),
+                          "wps_inner<2, %s>(s_dc_du, s_q, s_qd, %s, nullptr, S_WORK, gravity)" % (
+                              ("true", "s_qdd") if use_qdd_input else ("false", "nullptr")), device=True)
+            return
         if self._too_large("id_grad", "inverse_dynamics_gradient_device"):
             return
         self._serial_device_fn("Computes the gradient of inverse dynamics",
@@ -1102,10 +1161,10 @@ class GRiDCodeGenerator:
 
     # -- forward dynamics gradient
     def gen_forward_dynamics_gradient_inner_temp_mem_size(self):
-        return 0
+        return self._wide_temp_words() if self._wide("fd_grad") else 0
 
     def gen_forward_dynamics_gradient_kernel_max_temp_mem_size(self):
-        return 0
+        return self._wide_temp_words() if self._wide("fd_grad") else 0
 
     def gen_forward_dynamics_gradient_inner_python(self, use_thread_group=False, use_qdd_input=False):
         """The reference composes the FD gradient in Python out of the other inners
@@ -1114,6 +1173,14 @@ class GRiDCodeGenerator:
         self.gen_add_code_line("// df_du = -Minv*dc_du at qdd = FD(q,qd,u): one traced program (see *_device below)")
 
     def gen_forward_dynamics_gradient_device(self, use_thread_group=False, use_qdd_input=False):
+        if self._wide("fd_grad"):
+            self._wide_fn("Computes the gradient of forward dynamics",
+                          "void forward_dynamics_gradient_device(T *s_df_du, const T *s_q, const T *s_qd, %s"
+                          "const robotModel<T> *d_robotModel, const T gravity) {" % (
+                              "const T *s_qdd, const T *s_Minv, " if use_qdd_input else "const T *s_u, "),
+                          "wps_inner<3, %s>(s_df_du, s_q, s_qd, %s, S_WORK, gravity)" % (
+                              ("true", "s_qdd, s_Minv") if use_qdd_input else ("false", "s_u, nullptr")), device=True)
+            return
         if self._too_large("fd_grad", "forward_dynamics_gradient_device"):
             return
         sig = "void forward_dynamics_gradient_device(T *s_df_du, const T *s_q, const T *s_qd, %s" \

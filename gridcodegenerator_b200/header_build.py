@@ -14,9 +14,12 @@ HARNESS_SRC = os.path.join(ROOT, "tests", "header_harness.cu")
 def build_header_harness(robot_name: str = "iiwa14", force: bool = False, device_fns: bool = None,
                          timeout_s: int = 900) -> str:
     robot = load_named_robot(robot_name)
-    if device_fns is None:          # _inner/_device functions exist only where single-thread programs do
-        from .codegen import KernelPlan
-        device_fns = all("tps" in k for k in KernelPlan(robot).kind.values())
+    from .codegen import KernelPlan
+    kinds = KernelPlan(robot).kind
+    wide_fns = False
+    if device_fns is None:          # single-thread _inner/_device bodies, or the wide bodies behind the same names
+        device_fns = all("tps" in k for k in kinds.values())
+        wide_fns = not device_fns and all("tps" in k or "wps" in k for k in kinds.values())
     h = hashlib.sha256((_static_hash() + robot.param_hash()).encode())
     for fn in (HARNESS_SRC, os.path.join(os.path.dirname(__file__), "facade.py")):
         with open(fn, "rb") as f:
@@ -34,7 +37,8 @@ def build_header_harness(robot_name: str = "iiwa14", force: bool = False, device
     finally:
         os.chdir(cwd)
     cmd = [find_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-w",
-           "-I", hdr_dir, "-o", exe + ".tmp", HARNESS_SRC] + (["-DHARNESS_DEVICE_FNS"] if device_fns else [])
+           "-I", hdr_dir, "-o", exe + ".tmp", HARNESS_SRC] + (["-DHARNESS_DEVICE_FNS"] if device_fns else []) + (
+               ["-DHARNESS_WIDE_DEVICE_FNS"] if wide_fns else [])
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed on the emitted header:\n" + proc.stderr[-6000:])

@@ -31,7 +31,7 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence, Tuple
 
-from .algorithms import (RneaResult, SymRobot, cross_motion_axis, minv, minv_get, rnea,
+from .algorithms import (RneaResult, SymRobot, cross_motion_axis, fd_prologue, minv, minv_get, rnea,
                          rnea_grad_columns, vjp_column)
 from .ir import Program, V, dot
 from .robot import Robot
@@ -110,13 +110,10 @@ def _state_inputs(p: Program, n: int, ids: Sequence[int], block: int) -> List[V]
     return [p.inp("in:%d" % (block * n + g)) for g in ids]
 
 
-def _fd_prologue(p: Program, S: SymRobot, qd, u, g):
-    """RNEA(qdd = 0), Minv, qdd = Minv (u - c) of one component."""
-    nc = S.n
-    R0 = rnea(S, qd, None, g)
-    Mi = minv(S)
-    umc = [u[i] - R0.c[i] for i in range(nc)]
-    return Mi, [dot([minv_get(Mi, i, j) for j in range(nc)], umc) for i in range(nc)]
+def _fd_prologue(p: Program, S: SymRobot, qd, u, g, lam_v=None):
+    """RNEA(qdd = 0), Minv, qdd = Minv (u - c) of one component (+ w = Minv lam_v for the fused VJP)."""
+    _, Mi, qdd, extra = fd_prologue(S, qd, u, g, [lam_v] if lam_v is not None else [])
+    return (Mi, qdd, extra[0]) if lam_v is not None else (Mi, qdd)
 
 
 def _xnext_outputs(p: Program, n: int, ids: Sequence[int], q, qd, qdd, dt):
@@ -149,7 +146,11 @@ def _trace_stage_a(robot: Robot, ids: Sequence[int], alg: str, use_qdd: bool):
     Mi = None
     runs: List[Tuple[Tuple[int, ...], int]] = []
     ex = _Exports()
-    if alg in FD_LIKE:
+    if alg == "fd_vjp":
+        u = _state_inputs(p, n, ids, 2)
+        lam_q, lam_v = _state_inputs(p, n, ids, 3), _state_inputs(p, n, ids, 4)
+        Mi, qdd, w = _fd_prologue(p, S, qd, u, g, lam_v)
+    elif alg in FD_LIKE:
         u = _state_inputs(p, n, ids, 2)
         Mi, qdd = _fd_prologue(p, S, qd, u, g)
     else:
@@ -158,8 +159,6 @@ def _trace_stage_a(robot: Robot, ids: Sequence[int], alg: str, use_qdd: bool):
         dt = p.inp("dt")
         runs.append(_xnext_outputs(p, n, ids, q, qd, qdd, dt))
     if alg == "fd_vjp":
-        lam_q, lam_v = _state_inputs(p, n, ids, 3), _state_inputs(p, n, ids, 4)
-        w = [dot([minv_get(Mi, i, j) for j in range(nc)], lam_v) for i in range(nc)]
         for l, gid in enumerate(ids):
             p.output("out", 4 * n + gid, dt * w[l])
             ex.add("w%d" % l, w[l])
@@ -213,7 +212,10 @@ class _ImportSource:
 def _column_outputs(p: Program, n: int, ids: Sequence[int], j: int, cq, cqd, M):
     """Writes the two full output columns of local joint j (zeros outside the component)."""
     nc, base, jg = len(ids), ids[0], ids[j]
+    offs = []
     for s, col in ((0, cq), (1, cqd)):
+        if col is None:                              # this program computes only the other side
+            continue
         if M is None:
             vals = col
         else:
@@ -222,13 +224,17 @@ def _column_outputs(p: Program, n: int, ids: Sequence[int], j: int, cq, cqd, M):
         for ig in range(n):
             l = ig - base
             p.output("out", s * n * n + n * jg + ig, vals.get(l, 0.0) if 0 <= l < nc else 0.0)
-    return ((n * jg, n * n + n * jg), n)
+        offs.append(s * n * n + n * jg)
+    return (tuple(offs), n)
 
 
 def _lin_column_outputs(p: Program, n: int, ids: Sequence[int], j: int, cq, cqd, M, dt):
     """Columns jg of A21 = dt dqdd/dq and A22 = I + dt dqdd/dqd (zeros / identity outside the component)."""
     nc, base, jg = len(ids), ids[0], ids[j]
+    offs = []
     for s, col in ((0, cq), (1, cqd)):
+        if col is None:
+            continue
         rows = sorted(col)
         scaled = [col[r] * dt for r in rows]
         for ig in range(n):
@@ -237,29 +243,35 @@ def _lin_column_outputs(p: Program, n: int, ids: Sequence[int], j: int, cq, cqd,
             if s == 1 and ig == jg:
                 v = v + 1.0
             p.output("out", 2 * n + s * n * n + n * jg + ig, v)
-    return ((2 * n + n * jg, 2 * n + n * n + n * jg), n)
+        offs.append(2 * n + s * n * n + n * jg)
+    return (tuple(offs), n)
 
 
 def _consume_columns(p: Program, n: int, ids: Sequence[int], alg: str, columns, M, dt, w=None, lam_q=None, lam_v=None):
     """Turns the dc_du column pairs of `columns` into the output runs of `alg`."""
-    runs, done = [], []
+    runs, done, vjp_sides = [], [], (True, True)
     for j, cq, cqd in columns:
         if alg == "fd_vjp":
             aq, av = vjp_column(p, cq, cqd, w, lam_q[j], lam_v[j], dt)
-            p.output("out", 2 * n + ids[j], aq)
-            p.output("out", 3 * n + ids[j], av)
+            if aq is not None:
+                p.output("out", 2 * n + ids[j], aq)
+            if av is not None:
+                p.output("out", 3 * n + ids[j], av)
+            vjp_sides = (aq is not None, av is not None)
             done.append(j)
         elif alg == "fd_lin":
             runs.append(_lin_column_outputs(p, n, ids, j, cq, cqd, M, dt))
         else:
             runs.append(_column_outputs(p, n, ids, j, cq, cqd, M))
-    if done:                                         # a group holds contiguous joints: one run pair
+    if done:                                         # a group holds contiguous joints: one run (pair)
         assert done == list(range(done[0], done[0] + len(done)))
-        runs.append(((2 * n + ids[done[0]], 3 * n + ids[done[0]]), len(done)))
+        offs = tuple(off for off, on in ((2 * n + ids[done[0]], vjp_sides[0]), (3 * n + ids[done[0]], vjp_sides[1])) if on)
+        runs.append((offs, len(done)))
     return runs
 
 
-def _trace_stage_b(robot: Robot, ids: Sequence[int], sub: Robot, joints: Sequence[int], alg: str, ex: _Exports):
+def _trace_stage_b(robot: Robot, ids: Sequence[int], sub: Robot, joints: Sequence[int], alg: str, ex: _Exports,
+                   sides: Sequence[int] = (0, 1)):
     n, nc = robot.n, sub.n
     p = Program()
     imp = ex.importer(p)
@@ -275,8 +287,8 @@ def _trace_stage_b(robot: Robot, ids: Sequence[int], sub: Robot, joints: Sequenc
     if alg == "fd_vjp":
         kw = dict(w=[imp("w%d" % i) for i in range(nc)], lam_q={j: imp("lq%d" % j) for j in joints},
                   lam_v={j: imp("lv%d" % j) for j in joints})
-    runs = _consume_columns(p, n, ids, alg, rnea_grad_columns(S, qd, None, src=_ImportSource(imp), joints=joints),
-                            M, dt, **kw)
+    runs = _consume_columns(p, n, ids, alg, rnea_grad_columns(S, qd, None, src=_ImportSource(imp), joints=joints,
+                                                              sides=sides), M, dt, **kw)
     return p, runs
 
 
@@ -307,14 +319,16 @@ def _trace_full(robot: Robot, ids: Sequence[int], alg: str, use_qdd: bool):
         return p, [((base,), nc)]
     if alg == "fd":
         u = _state_inputs(p, n, ids, 2)
-        R = rnea(S, qd, None, g)
-        Mi = minv(S)
-        umc = [u[i] - R.c[i] for i in range(nc)]
+        _, qdd = _fd_prologue(p, S, qd, u, g)
         for i in range(nc):
-            p.output("out", ids[i], dot([minv_get(Mi, i, j) for j in range(nc)], umc))
+            p.output("out", ids[i], qdd[i])
         return p, [((base,), nc)]
     M, dt, kw = None, None, {}
-    if alg in FD_LIKE:
+    if alg == "fd_vjp":
+        u = _state_inputs(p, n, ids, 2)
+        lam_q, lam_v = _state_inputs(p, n, ids, 3), _state_inputs(p, n, ids, 4)
+        Mi, qdd, w = _fd_prologue(p, S, qd, u, g, lam_v)
+    elif alg in FD_LIKE:
         u = _state_inputs(p, n, ids, 2)
         Mi, qdd = _fd_prologue(p, S, qd, u, g)
         M = lambda r, c: minv_get(Mi, r, c)
@@ -324,8 +338,6 @@ def _trace_full(robot: Robot, ids: Sequence[int], alg: str, use_qdd: bool):
         dt = p.inp("dt")
         runs.append(_xnext_outputs(p, n, ids, q, qd, qdd, dt))
     if alg == "fd_vjp":
-        lam_q, lam_v = _state_inputs(p, n, ids, 3), _state_inputs(p, n, ids, 4)
-        w = [dot([minv_get(Mi, i, j) for j in range(nc)], lam_v) for i in range(nc)]
         for l, gid in enumerate(ids):
             p.output("out", 4 * n + gid, dt * w[l])
         runs.append(((4 * n + ids[0],), nc))
@@ -341,11 +353,14 @@ class PipeVariant:
     """All tasks of one algorithm variant of one robot, plus its scratch layout."""
 
     def __init__(self, robot: Robot, variant: str, single_stage_max_flops: int = 12000,
-                 group_flops: int = 6500, stage_a_max_flops: int = 20000):
+                 group_flops: int = 6500, stage_a_max_flops: int = 20000, split_sides_above: int = 0,
+                 struct_suffix: str = ""):
+        """split_sides_above: a single joint's column pair that costs more than this many flops is traced as two
+        programs, d/dq and d/dqd (0 = never)."""
         self.robot, self.variant = robot, variant
         sname, m0, m1, out_fn = PIPE_VARIANTS[variant]
         n = robot.n
-        self.struct = sname
+        self.struct = sname + struct_suffix
         self.in0, self.in1, self.out = m0 * n, m1 * n, out_fn(n)
         alg = {"id_qdd": "id", "id_grad_qdd": "id_grad"}.get(variant, variant)
         use_qdd = variant.endswith("_qdd")
@@ -381,12 +396,14 @@ class PipeVariant:
             btasks = []
             used: Dict[int, None] = {}
             for gi, J in enumerate(groups):
-                pb, runs = _trace_stage_b(robot, ids, sub, J, alg, ex)
-                live = pb.live_nodes()
-                for i, k in enumerate(pb.nodes):
-                    if live[i] and k[0] == "in" and k[1].startswith("sc:"):
-                        used[int(k[1][3:])] = None
-                btasks.append((gi, J, pb, runs))
+                too_long = split_sides_above and len(J) == 1 and cost[J[0]] > split_sides_above
+                for sides in (((0,), (1,)) if too_long else ((0, 1),)):
+                    pb, runs = _trace_stage_b(robot, ids, sub, J, alg, ex, sides)
+                    live = pb.live_nodes()
+                    for i, k in enumerate(pb.nodes):
+                        if live[i] and k[0] == "in" and k[1].startswith("sc:"):
+                            used[int(k[1][3:])] = None
+                    btasks.append(("%d%s" % (gi, "" if len(sides) == 2 else "qd"[sides[0]:sides[0] + 1] or "q"), J, pb, runs))
             # scratch words in stage-A production order
             word_of = {node: sc_base + w for w, node in enumerate(sorted(used))}
             sc_base += len(word_of)
@@ -397,7 +414,7 @@ class PipeVariant:
                 self.feasible = False
             self.tasks.append(ta)
             for gi, J, pb, runs in btasks:
-                t = PipeTask("c%d_B%d_j%d_%d" % (ci, gi, ids[J[0]], ids[J[-1]]), 1, pb, runs, ci)
+                t = PipeTask("c%d_B%s_j%d_%d" % (ci, gi, ids[J[0]], ids[J[-1]]), 1, pb, runs, ci)
                 if t.flops > stage_a_max_flops:          # a single column too long for one thread (64-link chain)
                     self.feasible = False
                 t.sc_word = {("sc:%d" % node): w for node, w in word_of.items()}

@@ -3,7 +3,7 @@ u ~ U(-20,20), qdd ~ U(-5,5), drawn in float64 and rounded to float32."""
 import numpy as np
 
 CONFIG_SEED_BASE = 20261018
-CONFIG_INDEX = {"iiwa14": 1, "hyq": 2, "atlas": 3, "chain64": 4, "mixed5": 5}
+CONFIG_INDEX = {"iiwa14": 1, "hyq": 2, "atlas": 3, "chain64": 4, "mixed5": 5, "pchain4": 6}
 
 
 def make_states(n: int, num_states: int, seed: int):

@@ -155,7 +155,7 @@ def load_urdf(path: str, name: Optional[str] = None) -> Robot:
         return parse_urdf_string(f.read(), name)
 
 
-NAMED_ROBOTS = ("iiwa14", "hyq", "atlas", "chain64", "mixed5")
+NAMED_ROBOTS = ("iiwa14", "hyq", "atlas", "chain64", "mixed5", "pchain4")
 
 
 def load_named_robot(name: str) -> Robot:

@@ -140,8 +140,8 @@ int grid_graph_launch(grid_graph *g, void *stream);
 void grid_graph_destroy(grid_graph *g);
 
 /* ---- options ------------------------------------------------------------------------------
- * The environment variables GRID_FORCE_KERNEL (tps|wps|cps|pipe), GRID_PIPE_MODE (staged|fused) and
- * GRID_PIPE_CHUNK (states) are read ONCE, at the first launch; afterwards they change only through
+ * The environment variables GRID_FORCE_KERNEL (tps|wps|cps|pipe), GRID_PIPE_MODE (staged|fused),
+ * GRID_PIPE_CHUNK (states) and GRID_PIPE_WARPS (CTA width of the phase-split kernels) are read ONCE, at the first launch; afterwards they change only through
  * this call (value NULL or "" restores the default).  Nothing on the launch path calls getenv. */
 int grid_set_option(const char *key, const char *value);
 

@@ -5,6 +5,8 @@
 // output: c, c_qdd, Minv, fd_qdd, dc_du, dc_du_qdd, df_du, df_du_pre, df_du_compute_only  (N states each)
 //         then device-function results for state 0: df_du_dev, dc_du_inner, Minv_inner, qdd_finish, c_inner,
 //         mxX(v1, k) for k = 0..5 (column 2 tripled), fx_times_v(v1, f1), fx(v1) * f1 via dot_prod
+//         wide robots (HARNESS_WIDE_DEVICE_FNS) instead: df_du_dev, dc_du_inner(vaf at qdd_in), dc_du_dev(qdd_in),
+//         Minv_inner, qdd_inner, df_du_dev(USE_QDD_MINV: FD's qdd, Minv)
 //         last (every robot): s_XImats (72 n) after load_update_XImats_helpers on state 0
 #include "grid.cuh"
 #include <vector>
@@ -71,6 +73,50 @@ __global__ void device_fn_kernel(T *out, const T *q_qd_u, const T *qdd_in, const
 
 #endif
 
+#ifdef HARNESS_WIDE_DEVICE_FNS
+// Robots whose single-thread programs are too large (Atlas, 64-link chain): the _inner/_device functions are the
+// wide CTA-per-state bodies behind the reference signatures.  _inner takes its scratch from the caller (s_temp,
+// <alg>_inner_temp_mem_size() floats = FD_DU_DYNAMIC_SHARED_MEM_COUNT here), _device uses the block's dynamic
+// shared memory; they run one after the other, so one dynamic block serves both.
+template <typename T>
+__global__ void __launch_bounds__(SUGGESTED_THREADS)
+wide_device_fn_kernel(T *out, const T *q_qd_u, const T *qdd_in, const robotModel<T> *d_robotModel, T gravity) {
+    constexpr int n = NUM_JOINTS;
+    extern __shared__ float4 s_dyn4[];
+    T *s_temp = reinterpret_cast<T *>(s_dyn4);
+    __shared__ T s_q[n], s_qd[n], s_u[n], s_qdd[n], s_c[n], s_vaf[18 * n], s_Minv[n * n], s_out[2 * n * n], s_fin[n];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        s_q[i] = q_qd_u[i]; s_qd[i] = q_qd_u[n + i]; s_u[i] = q_qd_u[2 * n + i]; s_qdd[i] = qdd_in[i];
+    }
+    __syncthreads();
+    T *o = out;
+    forward_dynamics_gradient_device<T>(s_out, s_q, s_qd, s_u, d_robotModel, gravity);          // df_du
+    for (int i = threadIdx.x; i < 2 * n * n; i += blockDim.x) o[i] = s_out[i];
+    o += 2 * n * n;
+    __syncthreads();
+    inverse_dynamics_inner<T>(s_c, s_vaf, s_q, s_qd, s_qdd, (T *)nullptr, (T *)nullptr, gravity); // v, a, f at qdd_in
+    inverse_dynamics_gradient_inner<T>(s_out, s_q, s_qd, s_vaf, (T *)nullptr, s_temp, gravity);  // dc_du from vaf
+    for (int i = threadIdx.x; i < 2 * n * n; i += blockDim.x) o[i] = s_out[i];
+    o += 2 * n * n;
+    __syncthreads();
+    inverse_dynamics_gradient_device<T>(s_out, s_q, s_qd, s_qdd, d_robotModel, gravity);         // dc_du (qdd given)
+    for (int i = threadIdx.x; i < 2 * n * n; i += blockDim.x) o[i] = s_out[i];
+    o += 2 * n * n;
+    __syncthreads();
+    direct_minv_inner<T>(s_Minv, s_q, (T *)nullptr, s_temp);
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) o[i] = s_Minv[i];
+    o += n * n;
+    __syncthreads();
+    forward_dynamics_inner<T>(s_fin, s_q, s_qd, s_u, (T *)nullptr, s_temp, gravity);             // qdd
+    for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = s_fin[i];
+    o += n;
+    __syncthreads();
+    // USE_QDD_MINV_FLAG overload fed with FD's own qdd and Minv: must reproduce df_du
+    forward_dynamics_gradient_device<T>(s_out, s_q, s_qd, s_fin, s_Minv, d_robotModel, gravity);
+    for (int i = threadIdx.x; i < 2 * n * n; i += blockDim.x) o[i] = s_out[i];
+}
+#endif
+
 int main(int argc, char **argv) {
     if (argc < 3) { fprintf(stderr, "usage: %s in.bin out.bin\n", argv[0]); return 2; }
     const int n = NUM_JOINTS;
@@ -130,6 +176,25 @@ int main(int argc, char **argv) {
     gpuErrchk(cudaMemcpy(dev.data(), d_dev, dev_words * sizeof(float), cudaMemcpyDeviceToHost));
     dump(dev.data(), dev_words);
     cudaFree(d_dev);
+#endif
+#ifdef HARNESS_WIDE_DEVICE_FNS
+    {
+        const size_t dev_words = 2 * n * n * 4 + n * n + n;
+        const size_t smem = FD_DU_DYNAMIC_SHARED_MEM_COUNT * sizeof(float);
+        float *d_dev, *d_qdd_in;
+        gpuErrchk(cudaMalloc(&d_dev, dev_words * sizeof(float)));
+        gpuErrchk(cudaMalloc(&d_qdd_in, n * sizeof(float)));
+        gpuErrchk(cudaMemcpy(d_qdd_in, qdd.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+        gpuErrchk(cudaFuncSetAttribute(wide_device_fn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wide_device_fn_kernel<float><<<1, SUGGESTED_THREADS, smem>>>(d_dev, hd->d_q_qd_u, d_qdd_in, d_robotModel, gravity);
+        gpuErrchk(cudaGetLastError());
+        gpuErrchk(cudaDeviceSynchronize());
+        std::vector<float> dev(dev_words);
+        gpuErrchk(cudaMemcpy(dev.data(), d_dev, dev_words * sizeof(float), cudaMemcpyDeviceToHost));
+        dump(dev.data(), dev_words);
+        cudaFree(d_dev);
+        cudaFree(d_qdd_in);
+    }
 #endif
     {
         float *d_xi;

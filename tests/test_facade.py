@@ -208,6 +208,14 @@ def test_emitted_header_host_and_device_functions_on_gpu(tmp_path, name, N):
             assert np.allclose(xi[n + i], robot.get_Imat_by_id(i), rtol=1e-6, atol=1e-7), i
 
     if name != "iiwa14":
+        # wide robots: _inner/_device are the CTA-per-state bodies behind the reference signatures (state 0)
+        assert relerr(take(2 * n * n, 1)[0], ref_fd_grad[0]) < TOL["fd_grad"]     # forward_dynamics_gradient_device
+        dc_qdd = O.colmajor(O.rnea_grad(robot, q64[0], qd64[0], qdd64[0]))
+        assert relerr(take(2 * n * n, 1)[0], dc_qdd) < TOL["id_grad"]             # inverse_dynamics_gradient_inner (vaf)
+        assert relerr(take(2 * n * n, 1)[0], dc_qdd) < TOL["id_grad"]             # inverse_dynamics_gradient_device
+        assert relerr(take(n * n, 1)[0], O.colmajor(O.minv(robot, q64[0], dense=False))) < TOL["minv"]
+        assert relerr(take(n, 1)[0], O.fd(robot, q64[0], qd64[0], u64[0])) < TOL["fd"]
+        assert relerr(take(2 * n * n, 1)[0], ref_fd_grad[0]) < TOL["fd_grad"]     # USE_QDD_MINV_FLAG device overload
         check_ximats()
         assert pos == data.size
         return

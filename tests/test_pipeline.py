@@ -81,3 +81,18 @@ def test_plan_policy():
         assert plan.kind["id"] == "tps"          # measured: the single-thread RNEA is faster (23 vs 31 us, Atlas 65 536)
     assert not PipeVariant(load_named_robot("chain64"), "id_grad").feasible
     assert KernelPlan(load_named_robot("chain64")).pipe == {}
+
+
+@pytest.mark.parametrize("variant", ["fd_grad", "id_grad", "fd_vjp", "fd_lin"])
+def test_side_split_and_two_stage_legs_are_exact(variant):
+    """Round-2 options of the phase-split decomposition - smaller column groups, two-stage legs, and the d/dq and
+    d/dqd columns of an expensive joint as separate programs - reproduce the default decomposition bit for bit
+    (float64 interpretation of the task programs)."""
+    robot = load_named_robot("atlas")
+    a = PipeVariant(robot, variant)
+    b = PipeVariant(robot, variant, group_flops=3000, single_stage_max_flops=4000, split_sides_above=3500)
+    assert len(b.tasks) > len(a.tasks) and any(t.name.endswith("q_j1_1") for t in b.tasks)
+    rows = np.random.default_rng(4).uniform(-1.5, 1.5, (3, a.in0 + a.in1))
+    oa, ob = a.evaluate(rows, dt=0.02), b.evaluate(rows, dt=0.02)
+    assert not np.isnan(ob).any() and np.array_equal(oa, ob)
+    assert max(t.flops for t in b.stage_tasks[1]) < 0.6 * max(t.flops for t in a.stage_tasks[1])

@@ -1,0 +1,106 @@
+#!/usr/bin/env python3
+"""Atlas FD-gradient experiments on the phase-split kernels: tagged library variants (fd_grad only) built
+here, timed on the B200.
+  python tools/atlas_variants.py build [names...]     (CPU, parallel nvcc)
+  python tools/atlas_variants.py run   [names...]     (GPU) -> JSON lines
+Every variant is checked against the C oracle on a sample before it is timed.
+"""
+import json
+import os
+import sys
+import time
+from concurrent.futures import ProcessPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from gridcodegenerator_b200 import load_named_robot                     # noqa: E402
+from gridcodegenerator_b200.build import build_robot_library            # noqa: E402
+from gridcodegenerator_b200.codegen import KernelPlan                   # noqa: E402
+
+ROBOT = os.environ.get("VARIANT_ROBOT", "atlas")
+ALG = "fd_grad"
+
+# name -> KernelPlan keyword arguments (only_algs is added to all)
+VARIANTS = {
+    "base":      dict(),
+    "g4000":     dict(pipe_opts=dict(group_flops=4000)),
+    "g3000":     dict(pipe_opts=dict(group_flops=3000)),
+    "g2000":     dict(pipe_opts=dict(group_flops=2000)),
+    "legs_g3000": dict(pipe_opts=dict(group_flops=3000, single_stage_max_flops=4000)),
+    "legs_g4500": dict(pipe_opts=dict(group_flops=4500, single_stage_max_flops=4000)),
+    "split_all": dict(pipe_opts=dict(group_flops=3000, single_stage_max_flops=4000, split_sides_above=3500)),
+    "split_g4500": dict(pipe_opts=dict(group_flops=4500, single_stage_max_flops=4000, split_sides_above=4500)),
+    "w4_g3000":  dict(pipe_opts=dict(group_flops=3000), pipe_warps=4, pipe_min_blocks=(2, 2)),
+    # 64-link chain, wide kernel: -Minv dc_du on the tensor cores (3xTF32 mma.sync) vs FP32 FFMA
+    "tc":        dict(wps_tc_matmul=True),
+    "notc":      dict(),
+    "s64":       dict(pipe_sync_every=64),
+    "s0":        dict(pipe_sync_every=0),
+}
+
+
+def plan_for(robot, name):
+    return KernelPlan(robot, only_algs=(ALG,), **VARIANTS[name])
+
+
+def _build(name):
+    robot = load_named_robot(ROBOT)
+    t = time.time()
+    so, info = build_robot_library(robot, plan_for(robot, name), tag="_x" + name)
+    spills = [l.strip() for l in info.get("ptxas", "").splitlines() if "spill" in l and " 0 bytes spill stores" not in l]
+    tasks = info.get("stats", {}).get("pipe_" + ALG, {})
+    return name, time.time() - t, len(spills), tasks.get("scratch_words"), len(tasks.get("tasks", [])), os.path.basename(so)
+
+
+def build(names):
+    with ProcessPoolExecutor(max_workers=int(os.environ.get("BUILD_JOBS", "5"))) as ex:
+        for r in ex.map(_build, names):
+            print("%-12s %6.1fs  kernels_with_spills=%d scratch_words=%s tasks=%s  %s" % r, flush=True)
+
+
+def run(names):
+    import numpy as np
+    import torch
+    from gridcodegenerator_b200.runtime import GridEngine
+    from gridcodegenerator_b200.synthetic import make_states, pack_q_qd_u
+    from oracle import c_oracle as C
+    robot = load_named_robot(ROBOT)
+    n = robot.n
+    NMAX = 65536 if ROBOT != "chain64" else 16384
+    q, qd, u, _ = make_states(n, NMAX, 3)
+    x = torch.from_numpy(pack_q_qd_u(q, qd, u)).cuda()
+    out = torch.empty(NMAX, 2 * n * n, device="cuda")
+    ref = C.batch(robot, ALG, q[:512], qd[:512], u[:512])
+    for name in names:
+        try:
+            eng = GridEngine(robot, plan=plan_for(robot, name), tag="_x" + name)
+            eng.forward_dynamics_gradient_device(out, x)
+            torch.cuda.synchronize()
+            err = float(np.abs(out[:512].cpu().numpy() - ref).max() / np.abs(ref).max())
+            res = {"variant": name, "plan": {k: (dict(v) if isinstance(v, dict) else v) for k, v in VARIANTS[name].items()},
+                   "relerr_vs_c_oracle": err}
+            if ROBOT == "chain64":
+                for N in (16384, 1024, 128):
+                    us = eng.time_launches(ALG, out, x, num_timesteps=N, stride=3 * n, reps=5 if N > 1000 else 20)
+                    res["us_N%d" % N] = float(np.median(us))
+                res["evals_per_s_N16384"] = 16384 / res["us_N16384"] * 1e6
+                print(json.dumps(res), flush=True)
+                continue
+            for N in (65536, 8192, 128):
+                us = eng.time_launches(ALG, out, x, num_timesteps=N, stride=3 * n, reps=20 if N > 1000 else 100)
+                res["us_N%d" % N] = float(np.median(us))
+            res["evals_per_s_N65536"] = 65536 / res["us_N65536"] * 1e6
+            for w in (8, 4, 2):                     # CTA width pinned (GRID_PIPE_WARPS) at the strong-scaling shard size
+                eng.set_option("GRID_PIPE_WARPS", str(w))
+                res["us_N8192_w%d" % w] = float(np.median(eng.time_launches(ALG, out, x, num_timesteps=8192, stride=3 * n, reps=20)))
+                res["us_N16384_w%d" % w] = float(np.median(eng.time_launches(ALG, out, x, num_timesteps=16384, stride=3 * n, reps=20)))
+            eng.set_option("GRID_PIPE_WARPS", None)
+            print(json.dumps(res), flush=True)
+        except Exception as e:
+            print(json.dumps({"variant": name, "error": str(e)[:300]}), flush=True)
+
+
+if __name__ == "__main__":
+    mode, names = sys.argv[1], sys.argv[2:] or list(VARIANTS)
+    (build if mode == "build" else run)(names)

@@ -28,11 +28,11 @@ def main():
         robot = load_named_robot(name)
         eng = get_engine(robot, tag=tag)
         n = robot.n
-        if family in ("tps", "wps", "cps", "pipe"):
+        if family in ("tps", "wps", "cps", "pipe", "lps"):
             os.environ["GRID_FORCE_KERNEL"] = family
         else:
             os.environ.pop("GRID_FORCE_KERNEL", None)
-        if family in ("tps", "wps", "cps", "pipe") and family not in eng.kernel_kind(alg):
+        if family in ("tps", "wps", "cps", "pipe", "lps") and family not in eng.kernel_kind(alg):
             print(json.dumps({"spec": spec, "skipped": "no %s kernel" % family}), flush=True)
             continue
         q, qd, u, _ = make_states(n, N, 3)
