@@ -542,17 +542,22 @@ grad_columns_kernel(float *__restrict__ d_out, const float *__restrict__ scratch
 constexpr int kColWarps = 8;
 constexpr int kChunkStates = 4096;     // scratch of a chunk: 4096 x N x 256 B (64-link chain: 67 MB, about half of L2)
 
-template <class K>
-static cudaError_t opt_in_smem(K kern, size_t bytes) {
-    static bool done[kMaxDevices];
+// shared-memory opt-in of a column kernel on the current device, once per (kernel, device).  Keyed by the
+// kernel's ADDRESS: the two gradient kernels have the same function type, a per-type static would be shared.
+static cudaError_t opt_in_smem(const void *kern, size_t bytes) {
+    constexpr int kMaxKernels = 8;
+    static const void *seen[kMaxDevices][kMaxKernels];
     int dev = 0;
     if (cudaError_t e = current_device(dev)) return e;
-    if (!done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return e;
-        done[dev] = true;
+    for (int i = 0; i < kMaxKernels; i++) {
+        if (seen[dev][i] == kern) return cudaSuccess;
+        if (seen[dev][i] == nullptr) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (e == cudaSuccess) seen[dev][i] = kern;       // benign race: idempotent
+            return e;
+        }
     }
-    return cudaSuccess;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 // ALG: 0 = Minv, 1 = FD, 2 = ID gradient (HAS_QDD: qdd given), 3 = FD gradient
@@ -564,9 +569,9 @@ cudaError_t lps_launch(float *d_out, const float *d_in, int stride, const float 
     constexpr int FLAGS = ALG == 0 ? 2 : ALG == 1 ? (1 | 2 | 4 | 32) : ALG == 2 ? (16 | (HAS_QDD ? 8 : 0)) : (1 | 2 | 4 | 16);
     constexpr size_t col_smem = sizeof(float) * N * PITCH * kColWarps;
     cudaError_t e = cudaSuccess;
-    if (ALG == 0) e = opt_in_smem(minv_columns_kernel<kColWarps>, col_smem);
-    if (ALG == 2) e = opt_in_smem(grad_columns_kernel<kColWarps, false>, col_smem);
-    if (ALG == 3) e = opt_in_smem(grad_columns_kernel<kColWarps, true>, col_smem);
+    if (ALG == 0) e = opt_in_smem((const void *)minv_columns_kernel<kColWarps>, col_smem);
+    if (ALG == 2) e = opt_in_smem((const void *)grad_columns_kernel<kColWarps, false>, col_smem);
+    if (ALG == 3) e = opt_in_smem((const void *)grad_columns_kernel<kColWarps, true>, col_smem);
     if (e != cudaSuccess) return e;
     const int chunk = num_states < kChunkStates ? num_states : kChunkStates;
     const size_t sc_bytes = (size_t)((chunk + 31) / 32) * N * W * 32 * sizeof(float);

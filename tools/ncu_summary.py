@@ -34,7 +34,10 @@ KEYS = [
 
 def main():
     rep, title = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else sys.argv[1])
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):        # already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv`): reports of the
+        txt = open(rep).read()      # Atlas library exceed the 64 MiB that gpurun copies back
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     name_i = hdr.index("Kernel Name")
