@@ -619,6 +619,8 @@ class KernelPlan:
                 if pv.feasible:
                     self.pipe[c] = pv
                     fams.append("pipe")
+            if "fd_grad" in self.lps:
+                fams.append("lps")
             self.consumers[c] = "+".join(fams) if fams else "none"
         self.cps_lanes = 16 if 2 * robot.n <= 16 else 32
         # where phase-split kernels exist they are at least as fast as the latency kernels at every batch
@@ -854,7 +856,16 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
         pipe_call = "pipe::pipe_launch<gen::%s>(d_out, d_in, stride, %s, N, g, s, dt)" % (pstruct, lam)
         tps_call = "tps_launch<%s, %d, %d>(d_out, d_in, stride, %s, nullptr, N, g, s, dt)" % (
             struct, W, plan.min_blocks["fd_grad"], lam)
-        if fam == "tps+pipe":
+        if "lps" in fam:
+            lps_call = "lps::lps_launch<%d, false>(d_out, d_in, stride, %s, N, g, s, dt)" % (4 if c == "fd_vjp" else 5, lam)
+            if fam == "lps":
+                L.append("    return %s;" % lps_call)
+            else:                                    # test builds of small chains: only when forced
+                L.append("    if (options().force_kernel == kLps) return %s;" % lps_call)
+            fam = fam.replace("+lps", "")
+        if fam == "lps":
+            pass
+        elif fam == "tps+pipe":
             L.append("    if (use_pipe(N)) return %s;" % pipe_call)
             L.append("    return %s;" % tps_call)
         elif fam == "pipe":
@@ -872,7 +883,7 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
         for a in plan.kind if "tps" in plan.kind[a] or "pipe" in plan.kind[a])
     fl += "\n" + "\n".join('    if (!strcmp(alg, "%s")) return %d;' % (
         c, stats[c]["flops"] if "tps" in fam else plan.pipe[c].flops)
-        for c, fam in plan.consumers.items() if fam != "none")
+        for c, fam in plan.consumers.items() if "tps" in fam or "pipe" in fam)
     out.append("#include <cstring>\n#include <cstdlib>\n")
     out.append(_LAUNCHERS % {"launchers": "\n".join(L), "kinds": kinds, "flops": fl})
     out.append('#include "grid_abi.cuh"\n')

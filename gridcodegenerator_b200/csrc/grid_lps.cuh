@@ -146,12 +146,17 @@ __device__ __forceinline__ void abi_to_parent(const Xf &X, const float *IA, cons
 // ---- stage A ------------------------------------------------------------------------------------
 // FLAGS: bit 0 = bias forces c (RNEA at qdd = 0), bit 1 = articulated-body inertias (U, Dinv),
 //        bit 2 = qdd = FD(q, qd, u) (needs bits 0 and 1), bit 3 = qdd given in d_qdd,
-//        bit 4 = gradient exports (RNEA at qdd -> mxS(X a_parent), mxS(f)), bit 5 = write qdd to d_qdd_out
+//        bit 4 = gradient exports (RNEA at qdd -> mxS(X a_parent), mxS(f)), bit 5 = write qdd to d_qdd_out,
+//        bit 6 = fused VJP consumer: second solve w = Minv lam_v (lam = d_qdd: [lam_q | lam_v] per state), w kept in
+//                the wY word for the column kernel, x+ and B^T lam = dt w written to d_qdd_out (5n words per state),
+//        bit 7 = fused linearisation consumer: x+ written to d_qdd_out (2n + 3n^2 words per state)
 template <int FLAGS>
 __global__ void __launch_bounds__(128)
 stage_a_kernel(const float *__restrict__ d_in, int stride, const float *__restrict__ d_qdd, float *__restrict__ scratch,
-               float *__restrict__ d_qdd_out, int num_states, float gravity) {
+               float *__restrict__ d_qdd_out, int num_states, float gravity, float dt) {
     constexpr bool C0 = FLAGS & 1, ABI = FLAGS & 2, SOLVE = FLAGS & 4, QDD_IN = FLAGS & 8, GRAD = FLAGS & 16, QDD_OUT = FLAGS & 32;
+    constexpr bool VJP = FLAGS & 64, LIN = FLAGS & 128;
+    constexpr int CONS_WORDS = VJP ? 5 * N : 2 * N + 3 * N * N;        // output row of a consumer
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int ntiles = (num_states + 31) >> 5;
@@ -233,6 +238,7 @@ stage_a_kernel(const float *__restrict__ d_in, int stride, const float *__restri
     // pass 2 (backward): c_i, articulated-body inertias, first half of the solve qdd = Minv (u - c)
     if (C0 || ABI) {
         float fc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Ft[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float Fw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};          // second right-hand side (VJP): lam_v
         float IAc[36];
 #pragma unroll
         for (int e = 0; e < 36; e++) IAc[e] = 0.f;
@@ -271,6 +277,13 @@ stage_a_kernel(const float *__restrict__ d_in, int stride, const float *__restri
 #pragma unroll
                     for (int r = 0; r < 6; r++) t[r] = fmaf(U[r], y, Ft[r]);
                     xtforce(X, t, Ft);
+                    if (VJP) {
+                        const float y2 = Dinv * (__ldg(d_qdd + st * 2 * N + N + i) - pick(Fw, k));
+                        sj[32 * wMXA] = y2;                    // free until pass 4
+#pragma unroll
+                        for (int r = 0; r < 6; r++) t[r] = fmaf(U[r], y2, Fw[r]);
+                        xtforce(X, t, Fw);
+                    }
                 }
                 if (i > 0) abi_to_parent(X, IA, U, Dinv, IAc);
             }
@@ -278,7 +291,7 @@ stage_a_kernel(const float *__restrict__ d_in, int stride, const float *__restri
     }
     // pass 3 (forward): second half of the solve
     if (SOLVE) {
-        float ap[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float ap[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, aw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int i = 0; i < N; i++) {
             const int k = wt_S[i];
             float *sj = joint_ptr(s, i);
@@ -289,11 +302,28 @@ stage_a_kernel(const float *__restrict__ d_in, int stride, const float *__restri
                 xmotion(X, ap, t);
 #pragma unroll
                 for (int r = 0; r < 6; r++) ap[r] = t[r];
+                if (VJP) {
+                    xmotion(X, aw, t);
+#pragma unroll
+                    for (int r = 0; r < 6; r++) aw[r] = t[r];
+                }
             }
-            const float qdd = sj[32 * wY] - sj[32 * wDINV] * dot6(U, ap);
+            const float Dinv = sj[32 * wDINV];
+            const float qdd = sj[32 * wY] - Dinv * dot6(U, ap);
             add_at(ap, k, qdd);
             sj[32 * wQDD] = qdd;
             if (QDD_OUT && valid) d_qdd_out[st * N + i] = qdd;
+            if (VJP) {
+                const float w = sj[32 * wMXA] - Dinv * dot6(U, aw);
+                add_at(aw, k, w);
+                sj[32 * wY] = w;                                // the column kernel reads w = Minv lam_v here
+                if (valid) d_qdd_out[st * CONS_WORDS + 4 * N + i] = dt * w;
+            }
+            if ((VJP || LIN) && valid) {                        // x+ = [q + dt qd ; qd + dt qdd]
+                const float q = __ldg(row + i), qd = sj[32 * wQD];
+                d_qdd_out[st * CONS_WORDS + i] = fmaf(dt, qd, q);
+                d_qdd_out[st * CONS_WORDS + N + i] = fmaf(dt, qdd, qd);
+            }
         }
     }
     // pass 4: RNEA at qdd -> mxS(X a_parent) and mxS(f)
@@ -360,9 +390,11 @@ __device__ __forceinline__ void store_rows(float *__restrict__ g_tile, long long
 // ---- Minv columns: warp = (32 states, column j) -----------------------------------------------------
 // replaces direct_minv_inner (algorithms/_direct_minv.py:23-382) for one column: F column backward from joint j
 // to the root, then forward from the root to j; rows below the diagonal are written as zeros.
-template <int WARPS>
+// LIN = false: d_Minv gets the upper-triangular, column-major Minv of the reference contract.
+// LIN = true (fused linearisation consumer): the block B2 = dt Minv, full symmetric, inside rows of 2n + 3n^2 words.
+template <int WARPS, bool LIN>
 __global__ void __launch_bounds__(32 * WARPS)
-minv_columns_kernel(float *__restrict__ d_Minv, const float *__restrict__ scratch, int num_states, int ntiles) {
+minv_columns_kernel(float *__restrict__ d_Minv, const float *__restrict__ scratch, int num_states, int ntiles, float dt) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *sa = smem + warp * (N * PITCH);
@@ -404,15 +436,29 @@ minv_columns_kernel(float *__restrict__ d_Minv, const float *__restrict__ scratc
         }
         add_at(G, k, m);
     }
-    for (int i = j + 1; i < N; i++) sa[i * PITCH + lane] = 0.f;
-    store_rows(d_Minv + (long long)tile * 32 * N * N, (long long)N * N, j * N, sa, N, cnt, lane);
+    if (!LIN) {
+        for (int i = j + 1; i < N; i++) sa[i * PITCH + lane] = 0.f;
+        store_rows(d_Minv + (long long)tile * 32 * N * N, (long long)N * N, j * N, sa, N, cnt, lane);
+    } else {
+        constexpr long long OUTW = 2 * N + 3 * N * N;
+        constexpr int B2 = 2 * N + 2 * N * N;
+        float *o = d_Minv + ((long long)tile * 32 + lane) * OUTW + B2;
+        if (lane < cnt)
+            for (int i = 0; i < j; i++) o[i * N + j] = dt * sa[i * PITCH + lane];   // mirror: row j of the columns i < j
+        for (int i = 0; i <= j; i++) sa[i * PITCH + lane] *= dt;
+        store_rows(d_Minv + (long long)tile * 32 * OUTW, OUTW, B2 + j * N, sa, j + 1, cnt, lane);
+    }
 }
 
 // ---- gradient columns: warp = (32 states, du-column) ---------------------------------------------------
-// SOLVE = false: dc_du column; true: df_du column = -Minv dc_du column through the articulated-body solve.
-template <int WARPS, bool SOLVE>
+// MODE 0: dc_du column; 1: df_du column = -Minv dc_du column through the articulated-body solve;
+//      2: fused VJP consumer: (A^T lam)[j] or (A^T lam)[n + j] = lam terms - dt dc_du[:, col] . w, w = Minv lam_v from stage A;
+//      3: fused linearisation consumer: column of A21 = dt dqdd/dq or A22 = I + dt dqdd/dqd.
+template <int WARPS, int MODE>
 __global__ void __launch_bounds__(32 * WARPS)
-grad_columns_kernel(float *__restrict__ d_out, const float *__restrict__ scratch, int num_states, int ntiles) {
+grad_columns_kernel(float *__restrict__ d_out, const float *__restrict__ scratch, const float *__restrict__ d_lam,
+                    int num_states, int ntiles, float dt) {
+    constexpr bool SOLVE = MODE == 1 || MODE == 3;
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *sa = smem + warp * (N * PITCH);
@@ -532,10 +578,25 @@ grad_columns_kernel(float *__restrict__ d_out, const float *__restrict__ scratch
                 x -= sj[32 * wDINV] * dot6(U, ap);
             }
             add_at(ap, k, x);
-            sa[i * PITCH + lane] = -x;
+            sa[i * PITCH + lane] = MODE == 3 ? fmaf(-dt, x, (side == 1 && i == j) ? 1.0f : 0.0f) : -x;
         }
     }
-    store_rows(d_out + (long long)tile * 32 * 2 * N * N, (long long)2 * N * N, side * N * N + j * N, sa, N, cnt, lane);
+    if (MODE == 2) {
+        float g = 0.f;
+        for (int i = 0; i < N; i++) g = fmaf(sa[i * PITCH + lane], s[(size_t)i * (W * 32) + 32 * wY], g);
+        if (lane < cnt) {
+            const long long st = (long long)tile * 32 + lane;
+            const float lq = __ldg(d_lam + st * 2 * N + j);
+            float *o = d_out + st * 5 * N;
+            if (side == 0) o[2 * N + j] = fmaf(-dt, g, lq);
+            else o[3 * N + j] = __ldg(d_lam + st * 2 * N + N + j) + dt * (lq - g);
+        }
+    } else if (MODE == 3) {
+        constexpr long long OUTW = 2 * N + 3 * N * N;
+        store_rows(d_out + (long long)tile * 32 * OUTW, OUTW, 2 * N + side * N * N + j * N, sa, N, cnt, lane);
+    } else {
+        store_rows(d_out + (long long)tile * 32 * 2 * N * N, (long long)2 * N * N, side * N * N + j * N, sa, N, cnt, lane);
+    }
 }
 
 // ---- launchers -------------------------------------------------------------------------------------------
@@ -560,18 +621,24 @@ static cudaError_t opt_in_smem(const void *kern, size_t bytes) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-// ALG: 0 = Minv, 1 = FD, 2 = ID gradient (HAS_QDD: qdd given), 3 = FD gradient
+// ALG: 0 = Minv, 1 = FD, 2 = ID gradient (HAS_QDD: qdd given), 3 = FD gradient,
+//      4 = fused VJP consumer (d_qdd = lambda, 2n per state; d_out rows of 5n), 5 = fused linearisation consumer
 template <int ALG, bool HAS_QDD>
 cudaError_t lps_launch(float *d_out, const float *d_in, int stride, const float *d_qdd, int num_states, float gravity,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, float dt = 0.f) {
     if (num_states <= 0) return cudaSuccess;
     g_calls.fetch_add(1);
-    constexpr int FLAGS = ALG == 0 ? 2 : ALG == 1 ? (1 | 2 | 4 | 32) : ALG == 2 ? (16 | (HAS_QDD ? 8 : 0)) : (1 | 2 | 4 | 16);
+    constexpr int FLAGS = ALG == 0 ? 2 : ALG == 1 ? (1 | 2 | 4 | 32) : ALG == 2 ? (16 | (HAS_QDD ? 8 : 0))
+                        : ALG == 3 ? (1 | 2 | 4 | 16) : ALG == 4 ? (1 | 2 | 4 | 16 | 64) : (1 | 2 | 4 | 16 | 128);
+    constexpr long long OUTW = ALG == 0 ? N * N : ALG == 1 ? N : ALG == 4 ? 5 * N : ALG == 5 ? 2 * N + 3 * N * N : 2 * N * N;
+    constexpr int QW = ALG == 4 ? 2 * N : N;              // words per state behind d_qdd (qdd or lambda)
     constexpr size_t col_smem = sizeof(float) * N * PITCH * kColWarps;
+    constexpr int GMODE = ALG == 3 ? 1 : ALG == 4 ? 2 : ALG == 5 ? 3 : 0;
+    auto minv_kern = minv_columns_kernel<kColWarps, ALG == 5>;
+    auto grad_kern = grad_columns_kernel<kColWarps, GMODE>;
     cudaError_t e = cudaSuccess;
-    if (ALG == 0) e = opt_in_smem((const void *)minv_columns_kernel<kColWarps>, col_smem);
-    if (ALG == 2) e = opt_in_smem((const void *)grad_columns_kernel<kColWarps, false>, col_smem);
-    if (ALG == 3) e = opt_in_smem((const void *)grad_columns_kernel<kColWarps, true>, col_smem);
+    if (ALG == 0 || ALG == 5) e = opt_in_smem((const void *)minv_kern, col_smem);
+    if (e == cudaSuccess && ALG >= 2) e = opt_in_smem((const void *)grad_kern, col_smem);
     if (e != cudaSuccess) return e;
     const int chunk = num_states < kChunkStates ? num_states : kChunkStates;
     const size_t sc_bytes = (size_t)((chunk + 31) / 32) * N * W * 32 * sizeof(float);
@@ -583,20 +650,21 @@ cudaError_t lps_launch(float *d_out, const float *d_in, int stride, const float 
         const int n = num_states - first < chunk ? num_states - first : chunk;
         const int ntiles = (n + 31) / 32;
         const float *in = d_in + (long long)first * stride;
-        const float *qdd = d_qdd ? d_qdd + (long long)first * N : nullptr;
+        const float *qdd = d_qdd ? d_qdd + (long long)first * QW : nullptr;
+        float *out = d_out + (long long)first * OUTW;
         stage_a_kernel<FLAGS><<<(ntiles + 3) / 4, 128, 0, stream>>>(in, stride, qdd, scratch,
-                                                                    ALG == 1 ? d_out + (long long)first * N : nullptr, n, gravity);
+                                                                    (ALG == 1 || ALG >= 4) ? out : nullptr, n, gravity, dt);
         g_kernel_launches.fetch_add(1);
         if ((e = cudaGetLastError()) != cudaSuccess) break;
-        if (ALG == 0) {
+        if (ALG == 0 || ALG == 5) {
             const long long tasks = (long long)N * ntiles;
-            minv_columns_kernel<kColWarps><<<(unsigned)((tasks + kColWarps - 1) / kColWarps), 32 * kColWarps, col_smem, stream>>>(
-                d_out + (long long)first * N * N, scratch, n, ntiles);
+            minv_kern<<<(unsigned)((tasks + kColWarps - 1) / kColWarps), 32 * kColWarps, col_smem, stream>>>(out, scratch, n, ntiles, dt);
             g_kernel_launches.fetch_add(1);
-        } else if (ALG >= 2) {
+            if ((e = cudaGetLastError()) != cudaSuccess) break;
+        }
+        if (ALG >= 2) {
             const long long blocks = (long long)((2 * N + kColWarps - 1) / kColWarps) * ntiles;
-            auto kern = ALG == 3 ? grad_columns_kernel<kColWarps, true> : grad_columns_kernel<kColWarps, false>;
-            kern<<<(unsigned)blocks, 32 * kColWarps, col_smem, stream>>>(d_out + (long long)first * 2 * N * N, scratch, n, ntiles);
+            grad_kern<<<(unsigned)blocks, 32 * kColWarps, col_smem, stream>>>(out, scratch, qdd, n, ntiles, dt);
             g_kernel_launches.fetch_add(1);
         }
         e = cudaGetLastError();

@@ -271,3 +271,46 @@ def test_results_outlive_their_grid_data():
     assert np.array_equal(view[:N], keep)          # close() never frees under a live view
     with pytest.raises(GridError, match="closed"):
         d2.forward_dynamics(N)
+
+
+# ---- consumers on the chain kernels (csrc/grid_lps.cuh) -----------------------------------------------
+@pytest.mark.parametrize("name", ["iiwa14", "pchain4"])
+@pytest.mark.parametrize("alg", ["fd_vjp", "fd_lin"])
+def test_consumers_on_chain_kernels_small_chains(name, alg, monkeypatch):
+    """The chain kernels' fused consumers (second articulated-body solve w = Minv lam_v in stage A, the dot with the
+    dc_du column in the column kernel; A21 / A22 columns and the mirrored B2 = dt Minv) forced onto small chains with
+    damping and prismatic joints: against the composed oracle, ragged last tile, chunked launch."""
+    import __graft_entry__ as G
+    robot = load_named_robot(name)
+    eng = GridEngine(robot, plan=G.lps_test_plan(robot), tag=G.LPS_TEST_TAG)
+    assert "lps" in eng.kernel_kind(alg)
+    monkeypatch.setenv("GRID_FORCE_KERNEL", "lps")
+    N = 4500
+    q, qd, u, _ = make_states(robot.n, N, seed_for(name) + 11)
+    lam = make_lambda(robot.n, N, 12)
+    out = run_consumer(eng, alg, q, qd, u, lam)
+    assert np.isfinite(out).all()
+    M = 128
+    ref = O.consumer_batch(robot, alg, q[:M].astype(np.float64), qd[:M].astype(np.float64), u[:M].astype(np.float64), DT,
+                           lam[:M].astype(np.float64))
+    assert blockwise_relerr(alg, robot.n, out[:M], ref) < TOL_CONSUMER, blockwise_relerr(alg, robot.n, out[:M], ref)
+    tail = O.consumer_batch(robot, alg, q[-3:].astype(np.float64), qd[-3:].astype(np.float64), u[-3:].astype(np.float64), DT,
+                            lam[-3:].astype(np.float64))
+    assert blockwise_relerr(alg, robot.n, out[-3:], tail) < TOL_CONSUMER
+    # the same values as the thread-per-state consumer programs of the default dispatch
+    monkeypatch.delenv("GRID_FORCE_KERNEL")
+    assert relerr(run_consumer(eng, alg, q[:M], qd[:M], u[:M], lam[:M]), out[:M]) < 1e-4
+
+
+@pytest.mark.parametrize("alg", ["fd_vjp", "fd_lin"])
+def test_consumers_chain64_against_c_oracle(alg):
+    """64-link chain: the fused consumers against the C oracle's pieces (fd, minv, fd_grad) composed on the host."""
+    robot = load_named_robot("chain64")
+    eng = get_engine(robot)
+    assert eng.kernel_kind(alg) == "lps"
+    N = 1024
+    q, qd, u, _ = make_states(robot.n, N, seed_for("chain64") + 13)
+    lam = make_lambda(robot.n, N, 14)
+    out = run_consumer(eng, alg, q, qd, u, lam)
+    ref = C.consumer_batch(robot, alg, q, qd, u, DT, lam.astype(np.float64))
+    assert blockwise_relerr(alg, robot.n, out, ref) < TOL_CONSUMER, blockwise_relerr(alg, robot.n, out, ref)
