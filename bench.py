@@ -181,7 +181,8 @@ def other_baseline_configs():
              ("cfg4_atlas_N65536", "atlas", ("fd_grad",), 65536),
              ("cfg4_atlas_N8192_per_gpu_of_8", "atlas", ("fd_grad",), 8192),
              ("cfg5_chain64_N65536", "chain64", ("id",), 65536),
-             ("cfg5_chain64_N4096", "chain64", ("fd_grad",), 4096)]
+             ("cfg5_chain64_N16384", "chain64", ("minv", "fd", "id_grad", "fd_grad"), 16384),
+             ("cfg5_chain64_N128", "chain64", ("fd_grad",), 128)]
     for key, name, algs, N in cases:
         try:
             robot = load_named_robot(name)

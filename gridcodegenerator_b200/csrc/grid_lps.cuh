@@ -59,6 +59,12 @@ constexpr int wS0 = 48;                // joint axis in base coordinates (motion
 constexpr int wU = 54, wDINV = 60;     // articulated-body U_i = IA_i S_i, 1 / (S_i^T U_i)
 constexpr int wQD = 61, wY = 62, wQDD = 63;
 constexpr int PITCH = 33;              // row pitch of the per-warp [joint][lane] staging tile
+constexpr int kColWarps = 8;
+// Stage A is latency-bound (one serial recursion per state; 218 us whether a launch holds 128 or 512 warps), so it
+// runs over chunks of 16 384 states; the column kernels walk a chunk in SUB-CHUNKS of 4 096 states (128 tiles) in
+// block order, so that the scratch lines they re-read ~20 times (67 MB per sub-chunk of the 64-link chain) stay in L2.
+constexpr int kSubTiles = 128;
+constexpr int kChunkStates = 4 * kSubTiles * 32;
 
 static std::atomic<long long> g_kernel_launches{0};
 static std::atomic<long long> g_calls{0};
@@ -398,9 +404,16 @@ minv_columns_kernel(float *__restrict__ d_Minv, const float *__restrict__ scratc
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *sa = smem + warp * (N * PITCH);
-    const long long task = (long long)blockIdx.x * WARPS + warp;       // column-major: long columns (large j) first
+    // sub-chunk major, then column-major (long columns = large j first), WARPS consecutive tiles per CTA
+    long long task = (long long)blockIdx.x * WARPS + warp;
     if (task >= (long long)N * ntiles) return;
-    const int j = N - 1 - (int)(task / ntiles), tile = (int)(task % ntiles);
+    int sub = 0, sub_tiles = min(kSubTiles, ntiles);
+    while (task >= (long long)N * sub_tiles) {
+        task -= (long long)N * sub_tiles;
+        sub++;
+        sub_tiles = min(kSubTiles, ntiles - sub * kSubTiles);
+    }
+    const int j = N - 1 - (int)(task / sub_tiles), tile = sub * kSubTiles + (int)(task % sub_tiles);
     const int cnt = min(32, num_states - tile * 32);
     const float *s = scratch + (size_t)tile * (N * W * 32) + lane;
     float F[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -450,12 +463,38 @@ minv_columns_kernel(float *__restrict__ d_Minv, const float *__restrict__ scratc
     }
 }
 
+// everything the gradient recursion reads per joint and state: 43 scratch words
+struct JointData {
+    Xf X, X0;
+    float v[6], iv[6], s0[6], qd;
+};
+__device__ __forceinline__ JointData load_joint(const float *sj) {
+    JointData d;
+    d.X = ldX(sj + 32 * wE);
+    ld6(sj + 32 * wV, d.v);
+    ld6(sj + 32 * wIV, d.iv);
+    d.qd = sj[32 * wQD];
+    ld6(sj + 32 * wS0, d.s0);
+    d.X0 = ldX(sj + 32 * wE0);
+    return d;
+}
+
 // ---- gradient columns: warp = (32 states, du-column) ---------------------------------------------------
 // MODE 0: dc_du column; 1: df_du column = -Minv dc_du column through the articulated-body solve;
 //      2: fused VJP consumer: (A^T lam)[j] or (A^T lam)[n + j] = lam terms - dt dc_du[:, col] . w, w = Minv lam_v from stage A;
 //      3: fused linearisation consumer: column of A21 = dt dqdd/dq or A22 = I + dt dqdd/dqd.
+// Measured on the 64-link chain (profiles/r2_lps_column_kernel_variants.jsonl, FD gradient of 16 384 states): occupancy
+// beats hand-made software pipelining - 3 CTAs per SM at 80 registers with the loads inside the iteration 2 614 us;
+// joint i + 1 requested before joint i is computed: 2 852 us at 2 CTAs / 128 registers (4 556 us when squeezed into 80),
+// unrolled by two 2 792 us, at 1 CTA / 158 registers 3 866 us.
+#ifndef GRID_LPS_PIPELINE
+#define GRID_LPS_PIPELINE 0            // 0: load inside the iteration, 1: request joint i + 1 before computing joint i, 2: + unroll by 2
+#endif
+#ifndef GRID_LPS_MINB
+#define GRID_LPS_MINB 3                // resident CTAs per SM the column kernel is compiled for (register cap 65536 / (256 * MINB))
+#endif
 template <int WARPS, int MODE>
-__global__ void __launch_bounds__(32 * WARPS)
+__global__ void __launch_bounds__(32 * WARPS, GRID_LPS_MINB)
 grad_columns_kernel(float *__restrict__ d_out, const float *__restrict__ scratch, const float *__restrict__ d_lam,
                     int num_states, int ntiles, float dt) {
     constexpr bool SOLVE = MODE == 1 || MODE == 3;
@@ -464,66 +503,84 @@ grad_columns_kernel(float *__restrict__ d_out, const float *__restrict__ scratch
     float *sa = smem + warp * (N * PITCH);
     // task order: joint-major, the two sides of a joint adjacent, long columns (small j) first; the WARPS warps
     // of a CTA take adjacent columns of ONE tile, so they read the same scratch lines at about the same time
-    const long long blk = blockIdx.x;
-    const int cgroups = (2 * N + WARPS - 1) / WARPS;
-    const int tile = (int)(blk % ntiles), cg = (int)(blk / ntiles);
+    constexpr int cgroups = (2 * N + WARPS - 1) / WARPS;
+    int blk = blockIdx.x, sub = 0, sub_tiles = min(kSubTiles, ntiles);
+    while (blk >= cgroups * sub_tiles) {            // sub-chunks of kSubTiles tiles, the last one may be shorter
+        blk -= cgroups * sub_tiles;
+        sub++;
+        sub_tiles = min(kSubTiles, ntiles - sub * kSubTiles);
+    }
+    const int tile = sub * kSubTiles + blk % sub_tiles, cg = blk / sub_tiles;
     const int cc = cg * WARPS + warp;
-    if (cg >= cgroups || cc >= 2 * N) return;
+    if (cc >= 2 * N) return;
     const int j = cc >> 1, side = cc & 1;
     const int cnt = min(32, num_states - tile * 32);
     const float *s = scratch + (size_t)tile * (N * W * 32) + lane;
 
+    // (GRID_LPS_PIPELINE > 0 requests the 43 scratch words of joint i + 1 before joint i is computed; the kernel is
+    // bound by exposed L1/L2 latency - long_scoreboard 4.4 stalls per issue, profiles/r2_ncu_lps_fdgrad_chain64_N4096.md -
+    // but the registers that costs lose more occupancy than the prefetch gains, see above.)
     float dv[6], da[6], P[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int i = j; i < N; i++) {
-        const int k = wt_S[i];
-        const float *sj = s + (size_t)i * (W * 32);
-        float v[6], iv[6], t[6];
-        ld6(sj + 32 * wV, v);
-        ld6(sj + 32 * wIV, iv);
-        const float qd = sj[32 * wQD];
-        if (i == j) {
-            if (side == 0) {
-                mxS(k, v, dv);                          // == mxS(X v_parent)
-                float mxa[6];
-                ld6(sj + 32 * wMXA, mxa);
-                mxS(k, dv, t);
-#pragma unroll
-                for (int r = 0; r < 6; r++) da[r] = fmaf(t[r], qd, mxa[r]);
-            } else {
-#pragma unroll
-                for (int r = 0; r < 6; r++) dv[r] = 0.f;
-                add_at(dv, k, 1.0f);
-                mxS(k, v, da);
-            }
-        } else {
-            const Xf X = ldX(sj + 32 * wE);
-            float n6[6];
-            xmotion(X, dv, n6);
-#pragma unroll
-            for (int r = 0; r < 6; r++) dv[r] = n6[r];
-            xmotion(X, da, n6);
+    JointData cur = load_joint(s + (size_t)j * (W * 32));
+    {   // joint j starts the column
+        const int k = wt_S[j];
+        const float *sj = s + (size_t)j * (W * 32);
+        float t[6];
+        if (side == 0) {
+            mxS(k, cur.v, dv);                              // == mxS(X v_parent)
+            float mxa[6];
+            ld6(sj + 32 * wMXA, mxa);
             mxS(k, dv, t);
 #pragma unroll
-            for (int r = 0; r < 6; r++) da[r] = fmaf(t[r], qd, n6[r]);
+            for (int r = 0; r < 6; r++) da[r] = fmaf(t[r], cur.qd, mxa[r]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 6; r++) dv[r] = 0.f;
+            add_at(dv, k, 1.0f);
+            mxS(k, cur.v, da);
+        }
+    }
+#if GRID_LPS_PIPELINE == 2
+#pragma unroll 2
+#else
+#pragma unroll 1
+#endif
+    for (int i = j; i < N; i++) {
+        const int k = wt_S[i];
+#if GRID_LPS_PIPELINE == 0
+        if (i > j) cur = load_joint(s + (size_t)i * (W * 32));
+        JointData nxt = cur;
+#else
+        JointData nxt = cur;
+        if (i + 1 < N) nxt = load_joint(s + (size_t)(i + 1) * (W * 32));
+#endif
+        float t[6];
+        if (i > j) {
+            float n6[6];
+            xmotion(cur.X, dv, n6);
+#pragma unroll
+            for (int r = 0; r < 6; r++) dv[r] = n6[r];
+            xmotion(cur.X, da, n6);
+            mxS(k, dv, t);
+#pragma unroll
+            for (int r = 0; r < 6; r++) da[r] = fmaf(t[r], cur.qd, n6[r]);
         }
         // df = I da + dv x* (I v) + v x* (I dv)
         float df[6], idv[6];
         imul(i, da, df);
-        crossf(dv, iv, t);
+        crossf(dv, cur.iv, t);
 #pragma unroll
         for (int r = 0; r < 6; r++) df[r] += t[r];
         imul(i, dv, idv);
-        crossf(v, idv, t);
+        crossf(cur.v, idv, t);
 #pragma unroll
         for (int r = 0; r < 6; r++) df[r] += t[r];
         // base-frame bookkeeping: keep s0_i . (forces of the joints before i), add this joint's force
-        float s0[6];
-        ld6(sj + 32 * wS0, s0);
-        sa[i * PITCH + lane] = dot6(s0, P);
-        const Xf X0 = ldX(sj + 32 * wE0);
-        xtforce(X0, df, t);
+        sa[i * PITCH + lane] = dot6(cur.s0, P);
+        xtforce(cur.X0, df, t);
 #pragma unroll
         for (int r = 0; r < 6; r++) P[r] += t[r];
+        cur = nxt;
     }
     // rows: i >= j: s0_i . (Total - prefix_i); i < j: s0_i . (Total - [dq] mxS(f_j) in the base frame)
     float T2[6];
@@ -538,6 +595,7 @@ grad_columns_kernel(float *__restrict__ d_out, const float *__restrict__ scratch
 #pragma unroll
         for (int r = 0; r < 6; r++) T2[r] -= t[r];
     }
+#pragma unroll 4
     for (int i = 0; i < N; i++) {
         const float *sj = s + (size_t)i * (W * 32);
         float s0[6];
@@ -549,6 +607,7 @@ grad_columns_kernel(float *__restrict__ d_out, const float *__restrict__ scratch
     if (SOLVE) {
         // x = Minv dc through the articulated-body recursions, then the column is -x
         float F[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
         for (int i = N - 1; i >= 0; i--) {
             const int k = wt_S[i];
             const float *sj = s + (size_t)i * (W * 32);
@@ -564,6 +623,7 @@ grad_columns_kernel(float *__restrict__ d_out, const float *__restrict__ scratch
             }
         }
         float ap[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
         for (int i = 0; i < N; i++) {
             const int k = wt_S[i];
             const float *sj = s + (size_t)i * (W * 32);
@@ -600,8 +660,6 @@ grad_columns_kernel(float *__restrict__ d_out, const float *__restrict__ scratch
 }
 
 // ---- launchers -------------------------------------------------------------------------------------------
-constexpr int kColWarps = 8;
-constexpr int kChunkStates = 4096;     // scratch of a chunk: 4096 x N x 256 B (64-link chain: 67 MB, about half of L2)
 
 // shared-memory opt-in of a column kernel on the current device, once per (kernel, device).  Keyed by the
 // kernel's ADDRESS: the two gradient kernels have the same function type, a per-type static would be shared.
