@@ -574,7 +574,7 @@ class KernelPlan:
         else:
             want = list(pipe_algs)
         variants = {"id": ("id", "id_qdd"), "minv": ("minv",), "fd": ("fd",), "id_grad": ("id_grad", "id_grad_qdd"),
-                    "fd_grad": ("fd_grad",)}
+                    "fd_grad": ("fd_grad", "fd_grad_qdd_minv")}
         for a in want:
             pvs = [PipeVariant(robot, v, **self.pipe_opts) for v in variants[a]]
             if all(pv.feasible for pv in pvs):
@@ -844,8 +844,11 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
                (None, "wps::wps_launch<3, false>(d_df_du, d_in, stride, nullptr, nullptr, N, g, s)")],
               [("!d_qdd", "cps_launch<gen::ColFdGrad, %d>(d_df_du, d_in, stride, nullptr, N, g, s)" % G)],
               pipe_call=([("!d_qdd && N <= %d" % plan.pipe_small_states, PL("PipeFdGradSmall", "d_df_du", "d_in", "nullptr"))]
-                         if plan.pipe_small else []) + [("!d_qdd", PL("PipeFdGrad", "d_df_du", "d_in", "nullptr"))],
-              lps_call=[("!d_qdd", "lps::lps_launch<3, false>(d_df_du, d_in, stride, nullptr, N, g, s)")])
+                         if plan.pipe_small else []) + [
+                  ("!d_qdd", PL("PipeFdGrad", "d_df_du", "d_in", "nullptr")),
+                  ("d_qdd", "pipe::pipe_launch<gen::PipeFdGradPre>(d_df_du, d_in, stride, d_qdd, N, g, s, 0.f, d_Minv)")],
+              lps_call=[("d_qdd", "lps::lps_launch<3, true>(d_df_du, d_in, stride, d_qdd, N, g, s, 0.f, d_Minv)"),
+                        (None, "lps::lps_launch<3, false>(d_df_du, d_in, stride, nullptr, N, g, s)")])
     L.append("}")
 
     for c, struct, pstruct, lam in (("fd_vjp", "AlgFdVjp", "PipeFdVjp", "d_lam"), ("fd_lin", "AlgFdLin", "PipeFdLin", "nullptr")):

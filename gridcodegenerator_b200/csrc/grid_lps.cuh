@@ -659,6 +659,80 @@ grad_columns_kernel(float *__restrict__ d_out, const float *__restrict__ scratch
     }
 }
 
+// ---- df_du = -Minv dc_du with a caller-supplied Minv (USE_QDD_MINV_FLAG overload) -------------------------------
+// The reference's overload takes qdd and Minv from the caller (algorithms/_forward_dynamics_gradient.py:22-25,
+// 202-220) and must use THAT Minv, so the O(n) solve of the column kernel does not apply: this is the one place
+// where the path has a real batched product, (n x n)(n x 2n) per state, and the one place tensor cores are used.
+// CTA = one state; Minv (column-major, upper triangle read symmetrically) and the dc_du block the column kernel left
+// in d_out are staged in shared memory with a padded pitch; N % 16 == 0: mma.sync.m16n8k8 TF32 with the 3xTF32 split
+// (FP32-class accuracy: 1.4e-6 relative at n = 64, 2x the FFMA rate with operands on chip,
+// profiles/r2_micro_tc_minv_gemm.jsonl); other N: FP32 FFMA, one thread per output column.
+template <int NN>
+__global__ void __launch_bounds__(NN % 16 == 0 ? 32 * (NN / 16) : 64)
+minv_product_kernel(float *__restrict__ d_out, const float *__restrict__ d_Minv, int num_states) {
+    constexpr int P = NN + 4;
+    extern __shared__ float smem[];
+    float *sA = smem, *sB = smem + NN * P;                       // A(row, k) = Minv, B(k, col) = dc at col * P + k
+    const int nthr = blockDim.x;
+    for (long long st = blockIdx.x; st < num_states; st += gridDim.x) {
+        const float *M = d_Minv + st * NN * NN;
+        float *o = d_out + st * 2 * NN * NN;
+        for (int e = threadIdx.x; e < NN * NN; e += nthr) {
+            const int c = e / NN, r = e - c * NN;                // column-major upper triangle -> full symmetric
+            if (r <= c) {
+                const float m = __ldg(M + e);
+                sA[r * P + c] = m;
+                sA[c * P + r] = m;
+            }
+        }
+        for (int e = threadIdx.x; e < 2 * NN * NN; e += nthr) sB[(e / NN) * P + e % NN] = o[e];
+        __syncthreads();
+        if constexpr (NN % 16 == 0) {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+            float acc[2 * NN / 8][4];
+#pragma unroll
+            for (int j = 0; j < 2 * NN / 8; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+            for (int k0 = 0; k0 < NN; k0 += 8) {
+                const float af[4] = {sA[(16 * warp + g) * P + k0 + t], sA[(16 * warp + g + 8) * P + k0 + t],
+                                     sA[(16 * warp + g) * P + k0 + t + 4], sA[(16 * warp + g + 8) * P + k0 + t + 4]};
+                unsigned ah[4], al[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    ah[i] = wps::to_tf32(af[i]);
+                    al[i] = wps::to_tf32(af[i] - __uint_as_float(ah[i]));
+                }
+#pragma unroll
+                for (int j = 0; j < 2 * NN / 8; j++) {
+                    const float bf[2] = {sB[(8 * j + g) * P + k0 + t], sB[(8 * j + g) * P + k0 + t + 4]};
+                    const unsigned bh[2] = {wps::to_tf32(bf[0]), wps::to_tf32(bf[1])};
+                    const unsigned bl[2] = {wps::to_tf32(bf[0] - __uint_as_float(bh[0])),
+                                            wps::to_tf32(bf[1] - __uint_as_float(bh[1]))};
+                    wps::mma_m16n8k8_tf32(acc[j], al, bh);
+                    wps::mma_m16n8k8_tf32(acc[j], ah, bl);
+                    wps::mma_m16n8k8_tf32(acc[j], ah, bh);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 2 * NN / 8; j++) {
+                const int c0 = 8 * j + 2 * t, r0 = 16 * warp + g;
+                o[c0 * NN + r0] = -acc[j][0];
+                o[(c0 + 1) * NN + r0] = -acc[j][1];
+                o[c0 * NN + r0 + 8] = -acc[j][2];
+                o[(c0 + 1) * NN + r0 + 8] = -acc[j][3];
+            }
+        } else {
+            for (int col = threadIdx.x; col < 2 * NN; col += nthr)
+                for (int r = 0; r < NN; r++) {
+                    float a = 0.f;
+                    for (int k = 0; k < NN; k++) a = fmaf(sA[r * P + k], sB[col * P + k], a);
+                    o[col * NN + r] = -a;
+                }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- launchers -------------------------------------------------------------------------------------------
 
 // shared-memory opt-in of a column kernel on the current device, once per (kernel, device).  Keyed by the
@@ -681,22 +755,29 @@ static cudaError_t opt_in_smem(const void *kern, size_t bytes) {
 
 // ALG: 0 = Minv, 1 = FD, 2 = ID gradient (HAS_QDD: qdd given), 3 = FD gradient,
 //      4 = fused VJP consumer (d_qdd = lambda, 2n per state; d_out rows of 5n), 5 = fused linearisation consumer
+//      ALG 3 with HAS_QDD: the USE_QDD_MINV_FLAG overload - dc_du columns at the given qdd, then the product with the
+//      caller's Minv (d_Minv) on the tensor cores (minv_product_kernel)
 template <int ALG, bool HAS_QDD>
 cudaError_t lps_launch(float *d_out, const float *d_in, int stride, const float *d_qdd, int num_states, float gravity,
-                       cudaStream_t stream, float dt = 0.f) {
+                       cudaStream_t stream, float dt = 0.f, const float *d_Minv = nullptr) {
     if (num_states <= 0) return cudaSuccess;
     g_calls.fetch_add(1);
-    constexpr int FLAGS = ALG == 0 ? 2 : ALG == 1 ? (1 | 2 | 4 | 32) : ALG == 2 ? (16 | (HAS_QDD ? 8 : 0))
+    constexpr bool PRE = ALG == 3 && HAS_QDD;
+    constexpr int FLAGS = ALG == 0 ? 2 : ALG == 1 ? (1 | 2 | 4 | 32) : (ALG == 2 || PRE) ? (16 | (HAS_QDD ? 8 : 0))
                         : ALG == 3 ? (1 | 2 | 4 | 16) : ALG == 4 ? (1 | 2 | 4 | 16 | 64) : (1 | 2 | 4 | 16 | 128);
     constexpr long long OUTW = ALG == 0 ? N * N : ALG == 1 ? N : ALG == 4 ? 5 * N : ALG == 5 ? 2 * N + 3 * N * N : 2 * N * N;
     constexpr int QW = ALG == 4 ? 2 * N : N;              // words per state behind d_qdd (qdd or lambda)
     constexpr size_t col_smem = sizeof(float) * N * PITCH * kColWarps;
-    constexpr int GMODE = ALG == 3 ? 1 : ALG == 4 ? 2 : ALG == 5 ? 3 : 0;
+    constexpr int GMODE = PRE ? 0 : ALG == 3 ? 1 : ALG == 4 ? 2 : ALG == 5 ? 3 : 0;
+    constexpr size_t prod_smem = sizeof(float) * 3 * N * (N + 4);
+    auto prod_kern = minv_product_kernel<N>;
+    if (PRE && !d_Minv) return cudaErrorInvalidValue;
     auto minv_kern = minv_columns_kernel<kColWarps, ALG == 5>;
     auto grad_kern = grad_columns_kernel<kColWarps, GMODE>;
     cudaError_t e = cudaSuccess;
     if (ALG == 0 || ALG == 5) e = opt_in_smem((const void *)minv_kern, col_smem);
     if (e == cudaSuccess && ALG >= 2) e = opt_in_smem((const void *)grad_kern, col_smem);
+    if (e == cudaSuccess && PRE) e = opt_in_smem((const void *)prod_kern, prod_smem);
     if (e != cudaSuccess) return e;
     const int chunk = num_states < kChunkStates ? num_states : kChunkStates;
     const size_t sc_bytes = (size_t)((chunk + 31) / 32) * N * W * 32 * sizeof(float);
@@ -724,6 +805,13 @@ cudaError_t lps_launch(float *d_out, const float *d_in, int stride, const float 
             const long long blocks = (long long)((2 * N + kColWarps - 1) / kColWarps) * ntiles;
             grad_kern<<<(unsigned)blocks, 32 * kColWarps, col_smem, stream>>>(out, scratch, qdd, n, ntiles, dt);
             g_kernel_launches.fetch_add(1);
+            if (PRE && (e = cudaGetLastError()) == cudaSuccess) {
+                int dev = 0, sms = 148;
+                if (current_device(dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                const int pb = n < 8 * sms ? n : 8 * sms;
+                prod_kern<<<pb, N % 16 == 0 ? 32 * (N / 16) : 64, prod_smem, stream>>>(out, d_Minv + (long long)first * N * N, n);
+                g_kernel_launches.fetch_add(1);
+            }
         }
         e = cudaGetLastError();
     }

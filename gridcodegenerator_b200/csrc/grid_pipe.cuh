@@ -132,7 +132,7 @@ template <class P, int STAGE>
 __global__ void __launch_bounds__(32 * P::WARPS, STAGE == 0 ? P::MINB0 : P::MINB1)
 pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0, const float *__restrict__ d_in1,
             float *__restrict__ scratch, unsigned int *__restrict__ ticket, int num_states, int ntiles, int nblk,
-            float gravity, float dt) {
+            float gravity, float dt, const float *__restrict__ d_in2) {
     using S = PipeShape<P>;
     constexpr int NTASKS = STAGE == 0 ? P::NTASKS0 : P::NTASKS1;
     extern __shared__ float smem_all[];
@@ -181,8 +181,10 @@ pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stri
         // private (scratch is allocated in whole tiles) and the flushes only write cnt states
         const int src = min(lane, cnt - 1);
         float *sc = scratch + (long long)tile * (P::SCRATCH_WORDS * 32) + lane;
+        // third input (the caller's Minv of the USE_QDD_MINV_FLAG overload): read by the lane straight from global
+        const float *g2 = P::IN2 > 0 ? d_in2 + (first + src) * (long long)P::IN2 : nullptr;
         P::template run<STAGE>(task, smem + src * S::IN_PAD, sc, sc, s_warp + lane * P::STAGE_PAD,
-                               d_out + first * P::OUT, owner ? cnt : 0, lane, s_warp, gravity, dt);
+                               d_out + first * P::OUT, owner ? cnt : 0, lane, s_warp, gravity, dt, g2);
         __syncwarp();
     }
 }
@@ -192,7 +194,8 @@ pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stri
 // (Atlas FD gradient at 8 192 states: 3 x 32 items of 8 tiles would occupy 96 of 148 SMs).
 template <class P, int STAGE>
 cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, const float *d_in1, float *scratch,
-                              unsigned int *ticket, int num_states, float gravity, cudaStream_t stream, float dt) {
+                              unsigned int *ticket, int num_states, float gravity, cudaStream_t stream, float dt,
+                              const float *d_in2) {
     using S = PipeShape<P>;
     constexpr int ntasks = STAGE == 0 ? P::NTASKS0 : P::NTASKS1;
     if (ntasks == 0) return cudaSuccess;
@@ -246,7 +249,7 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
     const int blocks = (int)(items < cap ? items : cap);
     kern<<<blocks, 32 * w, warp_smem * w, stream>>>(d_out, d_in0, stride0, d_in1, scratch,
                                                     items > cap ? ticket : nullptr, num_states, ntiles, nblk, gravity,
-                                                    dt);
+                                                    dt, d_in2);
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -271,7 +274,7 @@ template <class P>
 __global__ void __launch_bounds__(32 * P::WARPS, 1)
 pipe_fused_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0,
                   const float *__restrict__ d_in1, float *__restrict__ scratch, int *__restrict__ flags, int num_states,
-                  int ntiles, int nblk, float gravity, float dt, const PipePart part) {
+                  int ntiles, int nblk, float gravity, float dt, const PipePart part, const float *__restrict__ d_in2) {
     using S = PipeShape<P>;
     extern __shared__ float smem_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -305,12 +308,13 @@ pipe_fused_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, in
         __syncwarp();
         const int src = min(lane, cnt - 1);
         float *sc = scratch + (long long)tile * (P::SCRATCH_WORDS * 32) + lane;
+        const float *g2 = P::IN2 > 0 ? d_in2 + (first + src) * (long long)P::IN2 : nullptr;
         if (stage0)
             P::template run<0>(k, smem + src * S::IN_PAD, sc, sc, s_warp + lane * P::STAGE_PAD, d_out + first * P::OUT,
-                               owner ? cnt : 0, lane, s_warp, gravity, dt);
+                               owner ? cnt : 0, lane, s_warp, gravity, dt, g2);
         else
             P::template run<1>(k - P::NTASKS0, smem, sc, sc, s_warp + lane * P::STAGE_PAD, d_out + first * P::OUT,
-                               owner ? cnt : 0, lane, s_warp, gravity, dt);
+                               owner ? cnt : 0, lane, s_warp, gravity, dt, g2);
         if (stage0 && P::SCRATCH_WORDS > 0) {
             __threadfence();
             __syncwarp();
@@ -348,7 +352,7 @@ static int pipe_partition(int G, int nblk, PipePart &part) {
 
 template <class P>
 cudaError_t pipe_fused_launch(float *d_out, const float *d_in0, int stride0, const float *d_in1, int num_states,
-                              float gravity, cudaStream_t stream, bool &handled, float dt) {
+                              float gravity, cudaStream_t stream, bool &handled, float dt, const float *d_in2) {
     using S = PipeShape<P>;
     handled = false;
     auto kern = pipe_fused_kernel<P>;
@@ -384,7 +388,7 @@ cudaError_t pipe_fused_launch(float *d_out, const float *d_in0, int stride0, con
     if (e == cudaSuccess) {
         kern<<<blocks, 32 * P::WARPS, smem_bytes, stream>>>(d_out, d_in0, stride0, d_in1, (float *)buf,
                                                             (int *)(buf + sc_bytes), num_states, ntiles, nblk, gravity,
-                                                            dt, part);
+                                                            dt, part, d_in2);
         g_kernel_launches.fetch_add(1);
         e = cudaGetLastError();
     }
@@ -399,7 +403,7 @@ cudaError_t pipe_fused_launch(float *d_out, const float *d_in0, int stride0, con
 // Entry point: both stages on `stream` (or the experimental fused kernel, see below).
 template <class P>
 cudaError_t pipe_launch(float *d_out, const float *d_in0, int stride0, const float *d_in1, int num_states,
-                        float gravity, cudaStream_t stream, float dt = 0.f) {
+                        float gravity, cudaStream_t stream, float dt = 0.f, const float *d_in2 = nullptr) {
     if (num_states <= 0) return cudaSuccess;
     g_calls.fetch_add(1);
     float *scratch = nullptr;
@@ -411,7 +415,7 @@ cudaError_t pipe_launch(float *d_out, const float *d_in0, int stride0, const flo
     const bool fused = options().pipe_fused != 0;
     if (fused && P::NT > 1) {
         bool handled = false;
-        e = pipe_fused_launch<P>(d_out, d_in0, stride0, d_in1, num_states, gravity, stream, handled, dt);
+        e = pipe_fused_launch<P>(d_out, d_in0, stride0, d_in1, num_states, gravity, stream, handled, dt, d_in2);
         if (handled || e != cudaSuccess) return e;
     }
     // Two-stage variants can run in chunks of P::CHUNK_STATES states (a multiple of 32; GRID_PIPE_CHUNK
@@ -457,10 +461,11 @@ cudaError_t pipe_launch(float *d_out, const float *d_in0, int stride0, const flo
         float *o = d_out + (long long)first * P::OUT;
         const float *i0 = d_in0 + (long long)first * stride0;
         const float *i1 = d_in1 ? d_in1 + (long long)first * P::IN1 : nullptr;
-        e = pipe_stage_launch<P, 0>(o, i0, stride0, i1, sc, tickets ? tickets + 2 * c : nullptr, n, gravity, stream, dt);
+        const float *i2 = d_in2 ? d_in2 + (long long)first * P::IN2 : nullptr;
+        e = pipe_stage_launch<P, 0>(o, i0, stride0, i1, sc, tickets ? tickets + 2 * c : nullptr, n, gravity, stream, dt, i2);
         if (e == cudaSuccess)
             e = pipe_stage_launch<P, 1>(o, i0, stride0, i1, sc, tickets ? tickets + 2 * c + 1 : nullptr, n, gravity, stream,
-                                        dt);
+                                        dt, i2);
     }
     if (scratch) {
         cudaError_t e2 = cudaFreeAsync(scratch, stream);

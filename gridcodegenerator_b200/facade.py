@@ -920,10 +920,14 @@ class GRiDCodeGenerator:
         def sub(m):
             args = [a.strip() for a in m.group(1).split(",")]
             extras = args[3:args.index("d_robotModel")]
-            if len(extras) > 1 or (extras and names[1] is None):
-                return m.group(0)                      # no phase-split variant (USE_QDD_MINV_FLAG): wide kernel
-            struct = names[1] if extras else names[0]
             g = "gravity" if "gravity" in args else "0.f"
+            if len(extras) == 2 and alg_key == "fd_grad" and "fd_grad_qdd_minv" in self._plan.pipe:
+                # USE_QDD_MINV_FLAG: qdd through the tile, the caller's Minv read straight from global memory
+                return "gpuErrchk(%s::pipe::pipe_launch<%s::gen::PipeFdGradPre>(%s, %s, %s, %s, num_timesteps, %s, 0, 0.f, %s));" % (
+                    self._impl_ns, self._impl_ns, args[0], args[1], args[2], extras[0], g, extras[1])
+            if len(extras) > 1 or (extras and names[1] is None):
+                return m.group(0)                      # no phase-split variant: wide kernel
+            struct = names[1] if extras else names[0]
             return "gpuErrchk(%s::pipe::pipe_launch<%s::gen::%s>(%s, %s, %s, %s, num_timesteps, %s, 0));" % (
                 self._impl_ns, self._impl_ns, struct, args[0], args[1], args[2], extras[0] if extras else "nullptr", g)
         return re.sub(r"KERNEL<T><<<>>>\(([^;]*)\);", sub, line)

@@ -45,13 +45,23 @@ PIPE_VARIANTS = {
     "id_grad":     ("PipeIdGrad",     2, 0, lambda n: 2 * n * n),
     "id_grad_qdd": ("PipeIdGradQdd",  2, 1, lambda n: 2 * n * n),
     "fd_grad":     ("PipeFdGrad",     3, 0, lambda n: 2 * n * n),
+    # USE_QDD_MINV_FLAG overload (algorithms/_forward_dynamics_gradient.py:22-25, 202-220): in0 = [q | qd], in1 = qdd;
+    # the caller's Minv (n*n per state, column-major, upper triangle) is a third input that the state programs read
+    # straight from global memory ("g2:<index>") and hand to the column programs through the scratch array
+    "fd_grad_qdd_minv": ("PipeFdGradPre", 2, 1, lambda n: 2 * n * n),
     # consumers fused after the FD gradient (algorithms.trace_fd_consumer documents the outputs);
     # in1 = lam = [lam_q | lam_v]
     "fd_vjp":      ("PipeFdVjp",      3, 2, lambda n: 5 * n),
     "fd_lin":      ("PipeFdLin",      3, 0, lambda n: 2 * n + 3 * n * n),
 }
 FD_LIKE = ("fd_grad", "fd_vjp", "fd_lin")          # programs that start with RNEA(0), Minv, qdd
-GRAD_LIKE = ("id_grad",) + FD_LIKE                 # programs with du-columns (two-stage when large)
+GRAD_LIKE = ("id_grad", "fd_grad_pre") + FD_LIKE   # programs with du-columns (two-stage when large)
+
+
+def _given_minv(p: Program, n: int, ids: Sequence[int]):
+    """The caller's Minv restricted to one component, {(r, c): V} for local r <= c, read from the upper triangle of
+    the column-major n x n input (entries that couple different components are structural zeros and never read)."""
+    return {(r, c): p.inp("g2:%d" % (ids[c] * n + ids[r])) for c in range(len(ids)) for r in range(c + 1)}
 
 
 def components(robot: Robot) -> List[List[int]]:
@@ -153,6 +163,9 @@ def _trace_stage_a(robot: Robot, ids: Sequence[int], alg: str, use_qdd: bool):
     elif alg in FD_LIKE:
         u = _state_inputs(p, n, ids, 2)
         Mi, qdd = _fd_prologue(p, S, qd, u, g)
+    elif alg == "fd_grad_pre":
+        qdd = _state_inputs(p, n, ids, 2)                           # in1 follows the 2n words of in0
+        Mi = _given_minv(p, n, ids)
     else:
         qdd = _state_inputs(p, n, ids, 2) if use_qdd else None      # in1 follows the 2n words of in0
     if alg in ("fd_vjp", "fd_lin"):
@@ -281,7 +294,7 @@ def _trace_stage_b(robot: Robot, ids: Sequence[int], sub: Robot, joints: Sequenc
     q = [None if rev[i] else imp("q%d" % i) for i in range(nc)]
     S = SymRobot(p, sub, q, trig=(sin, cos))
     qd = [imp("qd%d" % i) for i in range(nc)]
-    M = (lambda r, c: imp("M%d_%d" % (min(r, c), max(r, c)))) if alg in ("fd_grad", "fd_lin") else None
+    M = (lambda r, c: imp("M%d_%d" % (min(r, c), max(r, c)))) if alg in ("fd_grad", "fd_lin", "fd_grad_pre") else None
     dt = p.inp("dt") if alg in ("fd_vjp", "fd_lin") else None
     kw = {}
     if alg == "fd_vjp":
@@ -332,6 +345,10 @@ def _trace_full(robot: Robot, ids: Sequence[int], alg: str, use_qdd: bool):
         u = _state_inputs(p, n, ids, 2)
         Mi, qdd = _fd_prologue(p, S, qd, u, g)
         M = lambda r, c: minv_get(Mi, r, c)
+    elif alg == "fd_grad_pre":
+        qdd = _state_inputs(p, n, ids, 2)
+        Mi = _given_minv(p, n, ids)
+        M = lambda r, c: minv_get(Mi, r, c)
     else:
         qdd = _state_inputs(p, n, ids, 2) if use_qdd else None
     if alg in ("fd_vjp", "fd_lin"):
@@ -362,8 +379,9 @@ class PipeVariant:
         n = robot.n
         self.struct = sname + struct_suffix
         self.in0, self.in1, self.out = m0 * n, m1 * n, out_fn(n)
-        alg = {"id_qdd": "id", "id_grad_qdd": "id_grad"}.get(variant, variant)
+        alg = {"id_qdd": "id", "id_grad_qdd": "id_grad", "fd_grad_qdd_minv": "fd_grad_pre"}.get(variant, variant)
         use_qdd = variant.endswith("_qdd")
+        self.in2 = n * n if alg == "fd_grad_pre" else 0
         self.tasks: List[PipeTask] = []
         self.scratch_words = 0
         self.feasible = True
@@ -424,7 +442,7 @@ class PipeVariant:
         self.stage_tasks = [sorted([t for t in self.tasks if t.stage == s], key=lambda t: -t.flops) for s in (0, 1)]
         self.flops = sum(t.flops for t in self.tasks)
 
-    def evaluate(self, in_rows, gravity: float = 9.81, dtype=None, dt: float = 0.0):
+    def evaluate(self, in_rows, gravity: float = 9.81, dtype=None, dt: float = 0.0, in2_rows=None):
         """Interprets the task programs with numpy in kernel order (stage 0, then stage 1) - the
         host-side check of the decomposition (tests/test_pipeline.py); never a product path.
         in_rows: (N, IN0 + IN1) array; returns (N, OUT) with NaN in words no task wrote."""
@@ -444,6 +462,8 @@ class PipeVariant:
                         inputs[name] = dtype(dt)
                     elif name.startswith("in:"):
                         inputs[name] = rows[:, int(name[3:])]
+                    elif name.startswith("g2:"):
+                        inputs[name] = np.asarray(in2_rows, dtype=dtype)[:, int(name[3:])]
                     else:
                         inputs[name] = scratch[:, t.sc_word[name]] if name in getattr(t, "sc_word", {}) else np.nan
                 res = t.program.evaluate(inputs, dtype=dtype)
@@ -491,6 +511,8 @@ def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead
             stmt, lead = "const float t%d = %s;" % (o, name), 0
         elif name.startswith("in:"):
             stmt, lead = "const float t%d = s_in[%d];" % (o, int(name[3:])), tile_lead
+        elif name.startswith("g2:"):
+            stmt, lead = "const float t%d = __ldg(g_in2 + %d);" % (o, int(name[3:])), scratch_lead
         else:
             stmt, lead = "const float t%d = pipe::ldsc(sc_in + %d);" % (o, 32 * sc_word[name]), scratch_lead
         load_pos[o] = max(0, fu - lead)
@@ -543,7 +565,8 @@ def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead
     body: List[str] = ["    // %s: %d mul + %d add per state" % (t.name, t.counts["mul"], t.counts["add"]),
                        "    static __device__ __noinline__ void %s(const float *s_in, const float *__restrict__ sc_in,"
                        " float *__restrict__ sc_out, float *s_stage, float *__restrict__ g_tile, const int cnt,"
-                       " const int lane, const float *s_warp, const float gravity, const float dt) {" % fname,
+                       " const int lane, const float *s_warp, const float gravity, const float dt,"
+                       " const float *__restrict__ g_in2) {" % fname,
                        # the call boundary hides the address space: without this the staging accesses
                        # compile to generic LD/ST instead of LDS/STS
                        indent + "__builtin_assume(__isShared(s_in)); __builtin_assume(__isShared(s_stage));"
@@ -608,8 +631,8 @@ def emit_pipe_struct(pv: PipeVariant, min_blocks: Tuple[int, int] = (1, 1), warp
     else:
         stage_pad = max_run | 1
     txt = ["struct %s {" % pv.struct,
-           "    static constexpr int IN0 = %d, IN1 = %d, OUT = %d, SCRATCH_WORDS = %d, STAGE_PAD = %d;" % (
-               pv.in0, pv.in1, pv.out, pv.scratch_words, stage_pad),
+           "    static constexpr int IN0 = %d, IN1 = %d, IN2 = %d, OUT = %d, SCRATCH_WORDS = %d, STAGE_PAD = %d;" % (
+               pv.in0, pv.in1, pv.in2, pv.out, pv.scratch_words, stage_pad),
            "    static constexpr int NTASKS0 = %d, NTASKS1 = %d, MINB0 = %d, MINB1 = %d, WARPS = %d;" % (
                len(pv.stage_tasks[0]), len(pv.stage_tasks[1]), min_blocks[0], min_blocks[1], warps),
            "    static constexpr long long TRACED_FLOPS = %d;" % pv.flops,
@@ -622,14 +645,14 @@ def emit_pipe_struct(pv: PipeVariant, min_blocks: Tuple[int, int] = (1, 1), warp
     txt.append("    template <int STAGE> static __device__ __forceinline__ void run(const int task, const float *s_in,"
                " const float *__restrict__ sc_in, float *__restrict__ sc_out, float *s_stage,"
                " float *__restrict__ g_tile, const int cnt, const int lane, const float *s_warp, const float gravity,"
-               " const float dt) {")
+               " const float dt, const float *__restrict__ g_in2) {")
     for s in (0, 1):
         if not pv.stage_tasks[s]:
             continue
         txt.append("        if (STAGE == %d) {" % s)
         txt.append("            switch (task) {")
         for ti in range(len(pv.stage_tasks[s])):
-            txt.append("            case %d: s%d_t%d(s_in, sc_in, sc_out, s_stage, g_tile, cnt, lane, s_warp, gravity, dt); break;"
+            txt.append("            case %d: s%d_t%d(s_in, sc_in, sc_out, s_stage, g_tile, cnt, lane, s_warp, gravity, dt, g_in2); break;"
                        % (ti, s, ti))
         txt.append("            default: break;")
         txt.append("            }")

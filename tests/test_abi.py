@@ -104,3 +104,22 @@ def test_sass_is_sm100a_and_barrier_free(iiwa_lib):
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", iiwa_lib], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_kernel_plan_families_per_robot():
+    """Which kernel family serves what: chain kernels only for serial chains without single-thread programs
+    (or when forced, for the test builds), fused consumers wherever the FD gradient has tps / pipe / lps kernels, a
+    second set of column programs for small Atlas batches, and `only_algs` for experiment builds."""
+    from gridcodegenerator_b200.codegen import KernelPlan
+    chain = KernelPlan(load_named_robot("chain64"))
+    assert chain.lps == {"minv", "fd", "id_grad", "fd_grad"} and chain.kind["id"] == "tps"
+    assert all(k.endswith("+lps") for a, k in chain.kind.items() if a != "id")
+    assert chain.consumers == {"fd_vjp": "lps", "fd_lin": "lps"}
+    iiwa = KernelPlan(load_named_robot("iiwa14"))
+    assert not iiwa.lps and iiwa.consumers == {"fd_vjp": "tps", "fd_lin": "tps"} and iiwa.pipe_small is None
+    forced = KernelPlan(load_named_robot("pchain4"), lps_force=True)
+    assert forced.lps and forced.lps_forced_only and "lps" in forced.consumers["fd_vjp"]
+    assert not KernelPlan(load_named_robot("mixed5"), lps_force=True).lps          # a tree is not a chain
+    atlas = KernelPlan(load_named_robot("atlas"), only_algs=("fd_grad",))
+    assert atlas.kind["minv"] == "none" and "pipe" in atlas.kind["fd_grad"] and atlas.consumers["fd_vjp"] == "none"
+    assert atlas.pipe_small is not None and len(atlas.pipe_small.tasks) > len(atlas.pipe["fd_grad"].tasks)

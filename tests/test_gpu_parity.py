@@ -407,6 +407,13 @@ def test_chain_kernels_on_small_chains(name, N, monkeypatch):
         assert relerr(out[:M], ref) < TOL[alg], (name, alg, relerr(out[:M], ref))
         per = np.abs(out[:M] - ref).max(axis=1) / np.abs(ref).max(axis=1)
         assert per.max() < 20 * TOL[alg], (name, alg, per.max())
+    # USE_QDD_MINV_FLAG overload: the CALLER's Minv must be used (here a deliberately scaled one), through the
+    # batched product kernel (tensor cores when n % 16 == 0, FFMA otherwise)
+    Md = np.array([1.25 * O.minv(robot, q64[s]) for s in range(M)])
+    Mu = np.array([np.triu(Md[s]).flatten(order="F") for s in range(M)], dtype=np.float32)
+    out = run_alg(eng, "fd_grad", q[:M], qd[:M], u[:M], qdd=qdd[:M], Minv=Mu)
+    ref = O.batch(robot, "fd_grad_qdd_minv", q64, qd64, qdd64, Minv_in=Md)
+    assert relerr(out, ref) < TOL["fd_grad"], (name, "fd_grad_qdd_minv", relerr(out, ref))
     # guard rows and batch-size independence
     big = run_alg(eng, "fd_grad", q, qd, u)
     guard = torch.full((N + 2, 2 * n * n), 7.0, device="cuda")
@@ -440,6 +447,18 @@ def test_chain64_chain_kernels_match_wide_kernels_and_oracle(monkeypatch):
         assert relerr(out[:64], wide) < TOL[alg], alg
         monkeypatch.delenv("GRID_FORCE_KERNEL")
         assert np.array_equal(run_alg(eng, alg, q[:512], qd[:512], u[:512]), out[:512])     # default = chain kernels
+    # USE_QDD_MINV_FLAG overload on the chain kernels: dc_du columns at the given qdd, then -Minv_given dc_du as a
+    # batched 3xTF32 tensor-core product; feeding FD's own qdd and Minv back must reproduce df_du
+    M = 512
+    qdd_fd = run_alg(eng, "fd", q[:M], qd[:M], u[:M])
+    Minv_fd = run_alg(eng, "minv", q[:M], qd[:M], u[:M])
+    ref = C.batch(robot, "fd_grad", q64[:M], qd64[:M], u64[:M])
+    pre = run_alg(eng, "fd_grad", q[:M], qd[:M], u[:M], qdd=qdd_fd, Minv=Minv_fd)
+    assert relerr(pre, ref) < TOL["fd_grad"], relerr(pre, ref)
+    monkeypatch.setenv("GRID_FORCE_KERNEL", "wps")
+    wide = run_alg(eng, "fd_grad", q[:32], qd[:32], u[:32], qdd=qdd_fd[:32], Minv=Minv_fd[:32])
+    monkeypatch.delenv("GRID_FORCE_KERNEL")
+    assert relerr(pre[:32], wide) < 1e-4
     N = 65536
     q, qd, u, _ = make_states(n, N, seed_for("chain64") + 6)
     out = run_alg(eng, "id", q, qd, u)
@@ -464,3 +483,34 @@ def test_atlas_fd_gradient_full_batch_65536_against_c_oracle():
     small = run_alg(eng, "fd_grad", q[:8192], qd[:8192], u[:8192])
     assert relerr(small, ref[:8192]) < TOL["fd_grad"]
     assert relerr(small, out[:8192]) < 1e-5
+
+
+@pytest.mark.parametrize("name,N", [("atlas", 3000), ("hyq", 1000), ("mixed5", 500)])
+def test_qdd_minv_overload_on_phase_split_kernels(name, N, monkeypatch):
+    """USE_QDD_MINV_FLAG on the phase-split kernels (round 1: 8x slower wide kernel for Atlas): qdd comes through the
+    input tile, the caller's Minv is read straight from global memory by the state programs and handed to the column
+    programs through the scratch array.  The CALLER's Minv must be used (a scaled one here); the wide kernel agrees."""
+    robot = load_named_robot(name)
+    eng = get_engine(robot) if name != "mixed5" else None
+    if eng is None:
+        import __graft_entry__ as G
+        from gridcodegenerator_b200.runtime import GridEngine
+        eng = GridEngine(robot, plan=G.split_test_plan(robot), tag=G.SPLIT_TEST_TAG)
+    assert "pipe" in eng.kernel_kind("fd_grad")
+    n = robot.n
+    q, qd, u, qdd = make_states(n, N, seed_for(name) + 21)
+    M = 48
+    q64, qd64, qdd64 = (x[:M].astype(np.float64) for x in (q, qd, qdd))
+    Md = np.array([0.8 * O.minv(robot, q64[s]) for s in range(M)])
+    Mu_small = np.array([np.triu(Md[s]).flatten(order="F") for s in range(M)], dtype=np.float32)
+    Mu = np.tile(Mu_small, (N // M + 1, 1))[:N].copy()
+    monkeypatch.setenv("GRID_FORCE_KERNEL", "pipe")
+    out = run_alg(eng, "fd_grad", q, qd, u, qdd=qdd, Minv=Mu)
+    ref = O.batch(robot, "fd_grad_qdd_minv", q64, qd64, qdd64, Minv_in=Md)
+    assert np.isfinite(out).all()
+    assert relerr(out[:M], ref) < TOL["fd_grad"], relerr(out[:M], ref)
+    monkeypatch.setenv("GRID_FORCE_KERNEL", "wps")
+    wide = run_alg(eng, "fd_grad", q[:M], qd[:M], u[:M], qdd=qdd[:M], Minv=Mu[:M])
+    assert relerr(out[:M], wide) < 1e-4
+    monkeypatch.delenv("GRID_FORCE_KERNEL")
+    assert np.array_equal(run_alg(eng, "fd_grad", q[:M], qd[:M], u[:M], qdd=qdd[:M], Minv=Mu[:M]), out[:M]) or name == "mixed5"

@@ -37,6 +37,13 @@ VARIANTS = {
     "notc":      dict(),
     "s64":       dict(pipe_sync_every=64),
     "s0":        dict(pipe_sync_every=0),
+    "s1024":     dict(pipe_sync_every=1024),
+    "w4_mb2":    dict(pipe_warps=4, pipe_min_blocks=(2, 2)),
+    "w4_mb2_s0": dict(pipe_warps=4, pipe_min_blocks=(2, 2), pipe_sync_every=0),
+    "w2_mb4_s0": dict(pipe_warps=2, pipe_min_blocks=(4, 4), pipe_sync_every=0),
+    "w1_mb8":    dict(pipe_warps=1, pipe_min_blocks=(8, 8)),
+    "lead320":   dict(pipe_scratch_lead=320),
+    "lead80":    dict(pipe_scratch_lead=80),
 }
 
 
