@@ -82,6 +82,8 @@ int grid_set_option(const char *key, const char *value) {
         o.pipe_chunk = unset ? -1 : atoi(value) / 32 * 32;
     } else if (!strcmp(key, "GRID_PIPE_WARPS")) {
         o.pipe_warps = unset ? 0 : atoi(value);
+    } else if (!strcmp(key, "GRID_PIPE_STAGGER_NS")) {
+        o.pipe_stagger_ns = unset ? 0 : atoi(value);
     } else {
         return GRID_NS::fail_msg("grid_set_option: unknown key");
     }

@@ -132,9 +132,20 @@ template <class P, int STAGE>
 __global__ void __launch_bounds__(32 * P::WARPS, STAGE == 0 ? P::MINB0 : P::MINB1)
 pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0, const float *__restrict__ d_in1,
             float *__restrict__ scratch, unsigned int *__restrict__ ticket, int num_states, int ntiles, int nblk,
-            float gravity, float dt, const float *__restrict__ d_in2) {
+            float gravity, float dt, const float *__restrict__ d_in2, int stagger_ns) {
     using S = PipeShape<P>;
     constexpr int NTASKS = STAGE == 0 ? P::NTASKS0 : P::NTASKS1;
+    // experiment (GRID_PIPE_STAGGER_NS): CTAs are placed round-robin over the SMs, so CTAs b, b + #SMs, ... share an
+    // SM; starting them apart de-phases their instruction streams
+    if (stagger_ns > 0) {
+        unsigned nsm;
+        asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+        for (unsigned w = (blockIdx.x / nsm) * (unsigned)stagger_ns; w > 0;) {
+            const unsigned step = w < 500000u ? w : 500000u;
+            __nanosleep(step);
+            w -= step;
+        }
+    }
     extern __shared__ float smem_all[];
     __shared__ int s_item;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -249,7 +260,7 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
     const int blocks = (int)(items < cap ? items : cap);
     kern<<<blocks, 32 * w, warp_smem * w, stream>>>(d_out, d_in0, stride0, d_in1, scratch,
                                                     items > cap ? ticket : nullptr, num_states, ntiles, nblk, gravity,
-                                                    dt, d_in2);
+                                                    dt, d_in2, options().pipe_stagger_ns);
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }

@@ -23,6 +23,7 @@ struct Options {
     int pipe_fused;         // 1 = experimental single-launch variant of the phase-split kernels
     int pipe_chunk;         // states per chunk of a two-stage launch; -1 = the compiled default
     int pipe_warps;         // warps per CTA of the phase-split kernels; 0 = chosen from the batch size
+    int pipe_stagger_ns;    // experiment: CTAs that share an SM start this many ns apart (de-phased instruction streams)
 };
 inline int parse_force(const char *f) {
     if (!f || !*f) return kAuto;
@@ -44,6 +45,8 @@ inline Options &options() {
         x.pipe_chunk = c ? atoi(c) / 32 * 32 : -1;
         const char *w = getenv("GRID_PIPE_WARPS");
         x.pipe_warps = w ? atoi(w) : 0;
+        const char *st = getenv("GRID_PIPE_STAGGER_NS");
+        x.pipe_stagger_ns = st ? atoi(st) : 0;
         return x;
     }();
     return o;

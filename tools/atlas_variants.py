@@ -103,6 +103,10 @@ def run(names):
                 res["us_N8192_w%d" % w] = float(np.median(eng.time_launches(ALG, out, x, num_timesteps=8192, stride=3 * n, reps=20)))
                 res["us_N16384_w%d" % w] = float(np.median(eng.time_launches(ALG, out, x, num_timesteps=16384, stride=3 * n, reps=20)))
             eng.set_option("GRID_PIPE_WARPS", None)
+            for ns in (2000, 10000, 40000):          # de-phased instruction streams: CTAs of one SM start ns apart
+                eng.set_option("GRID_PIPE_STAGGER_NS", str(ns))
+                res["us_N65536_stagger%d" % ns] = float(np.median(eng.time_launches(ALG, out, x, num_timesteps=65536, stride=3 * n, reps=10)))
+            eng.set_option("GRID_PIPE_STAGGER_NS", None)
             print(json.dumps(res), flush=True)
         except Exception as e:
             print(json.dumps({"variant": name, "error": str(e)[:300]}), flush=True)
