@@ -446,8 +446,10 @@ def trace_id_grad(robot: Robot, use_qdd: bool = False) -> Program:
     return p
 
 
-def trace_fd_grad(robot: Robot, use_qdd_minv: bool = False) -> Program:
-    """df_du = -Minv dc_du.  use_qdd_minv=False: inputs (q, qd, u), everything computed
+def trace_fd_grad(robot: Robot, use_qdd_minv: bool = False, side: Optional[int] = None) -> Program:
+    """df_du = -Minv dc_du.  side = 0 / 1: only the d/dq / d/dqd block (n*n words, output indices 0 .. n*n-1) - the
+    two halves of the mid-size-batch kernel (csrc/grid_tps.cuh tps_half_kernel), each with its own copy of the
+    column-independent part.  use_qdd_minv=False: inputs (q, qd, u), everything computed
     in one program.  True: inputs (q, qd, qdd, Minv) - the USE_QDD_MINV_FLAG overload
     (algorithms/_forward_dynamics_gradient.py:22-25, 202-220); Minv is read
     symmetrically from its upper triangle (algorithms/_forward_dynamics.py:44)."""
@@ -463,12 +465,14 @@ def trace_fd_grad(robot: Robot, use_qdd_minv: bool = False) -> Program:
         (u,) = _inputs(p, n, ("u",))
         _, Mi, qdd, _ = fd_prologue(sr, qd, u, g)
     R = rnea(sr, qd, qdd, g)
-    for j, cq, cqd in rnea_grad_columns(sr, qd, R):
+    for j, cq, cqd in rnea_grad_columns(sr, qd, R, sides=(0, 1) if side is None else (side,)):
         for s, col in ((0, cq), (1, cqd)):
+            if col is None:
+                continue
             rows = sorted(col)
             for i in range(n):
                 acc = dot([minv_get(Mi, i, r) for r in rows], [col[r] for r in rows])
-                p.output("df_du", s * n * n + n * j + i, -acc)
+                p.output("df_du", (s * n * n if side is None else 0) + n * j + i, -acc)
     return p
 
 
@@ -888,6 +892,8 @@ TRACERS = {
     "id_grad_qdd": lambda robot: trace_id_grad(robot, True),
     "fd_grad": lambda robot: trace_fd_grad(robot, False),
     "fd_grad_qdd_minv": lambda robot: trace_fd_grad(robot, True),
+    "fd_grad_q": lambda robot: trace_fd_grad(robot, False, side=0),
+    "fd_grad_qd": lambda robot: trace_fd_grad(robot, False, side=1),
     "fd_vjp": lambda robot: trace_fd_consumer(robot, "fd_vjp"),
     "fd_lin": lambda robot: trace_fd_consumer(robot, "fd_lin"),
 }

@@ -32,6 +32,9 @@ VARIANTS = {
     "id_grad_qdd":      ("AlgIdGradQdd",    2, 1, 0, "dc_du", lambda n: 2 * n * n),
     "fd_grad":          ("AlgFdGrad",       3, 0, 0, "df_du", lambda n: 2 * n * n),
     "fd_grad_qdd_minv": ("AlgFdGradPre",    2, 1, 1, "df_du", lambda n: 2 * n * n),
+    # the two halves of the mid-size-batch FD-gradient kernel (tps_half_kernel): d/dq block, d/dqd block
+    "fd_grad_q":        ("AlgFdGradQ",      3, 0, 0, "df_du", lambda n: n * n),
+    "fd_grad_qd":       ("AlgFdGradQd",     3, 0, 0, "df_du", lambda n: n * n),
     # consumers fused after the FD gradient (algorithms.trace_fd_consumer); in1 = lam (2n words)
     "fd_vjp":           ("AlgFdVjp",        3, 2, 0, "fd_vjp", lambda n: 5 * n),
     "fd_lin":           ("AlgFdLin",        3, 0, 0, "fd_lin", lambda n: 2 * n + 3 * n * n),
@@ -521,7 +524,8 @@ class KernelPlan:
                  pipe_opts: Optional[Dict[str, int]] = None, pipe_min_blocks: Tuple[int, int] = (1, 1),
                  pipe_warps: int = 8, pipe_sync_every: int = 256, pipe_scratch_lead: int = 160,
                  wps_tc_matmul: bool = False, only_algs=None, pipe_small_states: int = 24576,
-                 pipe_small_group_flops: int = 4000, lps_min_states: int = 256, lps_force: bool = False):
+                 pipe_small_group_flops: int = 4000, lps_min_states: int = 256, lps_force: bool = False,
+                 tps_half: bool = False):
         # every constructor argument except the robot: build.py hashes this into the library name, so
         # a library built with one plan is never returned for another
         self._args = {k: v for k, v in locals().items() if k not in ("self", "robot")}
@@ -605,6 +609,15 @@ class KernelPlan:
             pv = PipeVariant(robot, "fd_grad", group_flops=pipe_small_group_flops, struct_suffix="Small")
             if pv.feasible and len(pv.tasks) > len(self.pipe["fd_grad"].tasks):
                 self.pipe_small = pv
+        # EXPERIMENT (off; measured slower): mid-size batches of a thread-per-state FD gradient (between the latency
+        # kernels and one tile per resident warp) with a warp per (tile, half) - the d/dq or the d/dqd block, each with
+        # its own copy of the column-independent part: critical path 0.61x (6 490 / 5 906 vs 10 606 traced flops), twice
+        # the warps in flight.  iiwa14, 4 096 ... 18 944 states: 22.9-24.9 us vs 20.8 us for the whole program per
+        # thread (profiles/r2_exp_tps_half_split.jsonl).  The ~20 us of a single pass is not the dependent chain of one
+        # warp but the cold stream of the program's code through every SM (139 KB at ~3.5 B/cycle); two half programs
+        # are 1.17x the code.
+        self.tps_half = (bool(tps_half) and "tps" in self.kind["fd_grad"] and "pipe" not in self.kind["fd_grad"]
+                         and plan_default(tps_warps, tps_v2_park, tps_loop_columns, tps_pairs))
         # consumers fused after the FD gradient ride on the family that serves fd_grad at large batches
         self.consumers: Dict[str, str] = {}
         for c in ("fd_vjp", "fd_lin"):
@@ -636,6 +649,11 @@ class KernelPlan:
         self.min_blocks = {"id": 16, "minv": 16, "fd": 16, "id_grad": 8, "fd_grad": 8}
         if tps_min_blocks:
             self.min_blocks.update(tps_min_blocks)
+
+
+def plan_default(tps_warps, tps_v2_park, tps_loop_columns, tps_pairs) -> bool:
+    """The half-split kernel is only generated beside the default thread-per-state programs."""
+    return tps_warps == 1 and tps_v2_park is None and not tps_loop_columns and not tps_pairs
 
 
 def plan_signature(plan: Optional["KernelPlan"]) -> str:
@@ -716,6 +734,11 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
             txt, cnt = emit_alg_struct(robot, c, sync_every=plan.tps_sync_every)
             out.append(txt)
             stats[c] = cnt
+    if plan.tps_half:
+        for v in ("fd_grad_q", "fd_grad_qd"):
+            txt, cnt = emit_alg_struct(robot, v)
+            out.append(txt)
+            stats[v] = cnt
     has_cps = any("cps" in k for k in plan.kind.values())
     if has_cps:
         for nm, alg, uq in (("ColIdGrad", "id_grad", False), ("ColIdGradQdd", "id_grad", True),
@@ -837,9 +860,12 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
     L.append("}")
     L.append("cudaError_t launch_fd_grad(float *d_df_du, const float *d_in, int stride, const float *d_qdd,"
              " const float *d_Minv, int N, float g, cudaStream_t s) {")
+    half = ([("!d_qdd && options().force_kernel == kAuto && tps_half_fits<AlgFdGradQ, AlgFdGradQd, %d>(N)" % plan.min_blocks["fd_grad"],
+              "tps_half_launch<AlgFdGradQ, AlgFdGradQd, %d>(d_df_du, d_in, stride, N, g, s)" % plan.min_blocks["fd_grad"])]
+            if plan.tps_half else [])
     L += body("fd_grad",
-              [("d_qdd", "%s(d_df_du, d_in, stride, d_qdd, d_Minv, N, g, s)" % tps("fd_grad", "AlgFdGradPre")),
-               (None, "%s(d_df_du, d_in, stride, nullptr, nullptr, N, g, s)" % tps("fd_grad", "AlgFdGrad"))],
+              [("d_qdd", "%s(d_df_du, d_in, stride, d_qdd, d_Minv, N, g, s)" % tps("fd_grad", "AlgFdGradPre"))] + half +
+              [(None, "%s(d_df_du, d_in, stride, nullptr, nullptr, N, g, s)" % tps("fd_grad", "AlgFdGrad"))],
               [("d_qdd", "wps::wps_launch<3, true>(d_df_du, d_in, stride, d_qdd, d_Minv, N, g, s)"),
                (None, "wps::wps_launch<3, false>(d_df_du, d_in, stride, nullptr, nullptr, N, g, s)")],
               [("!d_qdd", "cps_launch<gen::ColFdGrad, %d>(d_df_du, d_in, stride, nullptr, N, g, s)" % G)],

@@ -190,6 +190,75 @@ tps_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int strid
     tps_body<A>(d_out, d_in0, stride0, d_in1, d_in2, num_states, gravity, dt);
 }
 
+// ---- mid-size batches: (tile, half) per warp ---------------------------------------------------------------
+// A0 / A1 compute the d/dq / d/dqd block of the FD gradient (OUT = n*n words each, the column-independent part
+// duplicated).  Work item = (tile, half); the output row of a state is 2 * OUT words, a half owns OUT of them.
+template <class A0, class A1, int MIN_BLOCKS>
+__global__ void __launch_bounds__(32, MIN_BLOCKS)
+tps_half_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0, int num_states, float gravity) {
+    using S = TpsShape<A0>;
+    static_assert(A0::IN0 == A1::IN0 && A0::OUT == A1::OUT && A0::IN1 == 0 && A1::IN1 == 0, "halves must match");
+    extern __shared__ float smem[];
+    float *sw = smem;
+    const int lane = threadIdx.x & 31;
+    const int ntiles = (num_states + 31) >> 5;
+    for (int item = blockIdx.x; item < 2 * ntiles; item += gridDim.x) {
+        const int tile = item >> 1, half = item & 1;
+        const long long first = (long long)tile * 32;
+        const int cnt = max(0, min(32, num_states - (int)first));
+        const float *src0 = d_in0 + first * (long long)stride0;
+        if (S::IN_LINEAR && stride0 == A0::IN0 && aligned16(src0)) warp_copy_g2s(sw, src0, cnt * A0::IN0, lane);
+        else tile_load<A0::IN0, S::IN_PAD>(sw, 0, d_in0, first, stride0, cnt, lane);
+        __syncwarp();
+        const int src = max(0, min(lane, cnt - 1));
+        if (half == 0) A0::eval(sw + src * S::IN_PAD, sw + lane * S::OUT_PAD, gravity, 0.f);
+        else A1::eval(sw + src * S::IN_PAD, sw + lane * S::OUT_PAD, gravity, 0.f);
+        __syncwarp();
+        float *dst = d_out + first * (2 * A0::OUT) + half * A0::OUT;
+        for (int e = lane; e < cnt * A0::OUT; e += 32) {
+            const int st = e / A0::OUT, k = e - st * A0::OUT;
+            dst[(long long)st * (2 * A0::OUT) + k] = sw[st * S::OUT_PAD + k];
+        }
+        __syncwarp();
+    }
+}
+
+// resident single-warp CTAs of the half kernel on the current device (0 on error)
+template <class A0, class A1, int MIN_BLOCKS>
+static int tps_half_cap() {
+    using S = TpsShape<A0>;
+    auto kern = tps_half_kernel<A0, A1, MIN_BLOCKS>;
+    constexpr size_t smem_bytes = sizeof(float) * S::WARP_WORDS;
+    static int caps[kMaxDevices];
+    int dev = 0;
+    if (current_device(dev) != cudaSuccess) return 0;
+    if (caps[dev] == 0) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return 0;
+        int sms = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem_bytes);
+        caps[dev] = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    return caps[dev];
+}
+// the split pays while every (tile, half) item has its own resident warp
+template <class A0, class A1, int MIN_BLOCKS>
+static bool tps_half_fits(int num_states) {
+    const int cap = tps_half_cap<A0, A1, MIN_BLOCKS>();
+    return cap > 0 && 2 * ((num_states + 31) / 32) <= cap;
+}
+template <class A0, class A1, int MIN_BLOCKS>
+cudaError_t tps_half_launch(float *d_out, const float *d_in0, int stride0, int num_states, float gravity, cudaStream_t stream) {
+    using S = TpsShape<A0>;
+    if (num_states <= 0) return cudaSuccess;
+    const int cap = tps_half_cap<A0, A1, MIN_BLOCKS>();
+    if (cap <= 0) return cudaErrorLaunchOutOfResources;
+    const int items = 2 * ((num_states + 31) / 32);
+    tps_half_kernel<A0, A1, MIN_BLOCKS><<<items < cap ? items : cap, 32, sizeof(float) * S::WARP_WORDS, stream>>>(
+        d_out, d_in0, stride0, num_states, gravity);
+    return cudaGetLastError();
+}
+
 // ---- variant 2: per-column output flush + parked per-state data ------------------------------
 // The gradient programs can park long-lived per-joint values in a lane-private shared-memory
 // column (slot-major, conflict-free) and re-load them in every du-column, and they flush each

@@ -40,6 +40,11 @@ def _run(robot, key, q, qd, u, qdd, dtype):
         Md = np.array([O.minv(robot, q[s]) for s in range(N)])
         return (p.evaluate(_ins(q=q, qd=qd, qdd=qdd, Minv=Mu), dtype)["df_du"],
                 O.batch(robot, "fd_grad_qdd_minv", q, qd, qdd, Minv_in=Md), "fd_grad")
+    if key in ("fd_grad_q", "fd_grad_qd"):       # the halves of the mid-size-batch kernel: d/dq block, d/dqd block
+        nn = robot.n * robot.n
+        ref = O.batch(robot, "fd_grad", q, qd, u)
+        return (p.evaluate(_ins(q=q, qd=qd, u=u), dtype)["df_du"],
+                ref[:, :nn] if key == "fd_grad_q" else ref[:, nn:], "fd_grad")
     if key in ("fd_vjp", "fd_lin"):              # consumers fused after the FD gradient
         lam = np.random.default_rng(2).uniform(-3, 3, (N, 2 * robot.n))
         ins = _ins(q=q, qd=qd, u=u, lam=lam)
