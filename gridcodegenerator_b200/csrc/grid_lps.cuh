@@ -659,6 +659,200 @@ grad_columns_kernel(float *__restrict__ d_out, const float *__restrict__ scratch
     }
 }
 
+// ---- gradient columns, CTA-cooperative: joint blocks streamed into shared memory by the bulk-copy engine (TMA) ----
+// The column kernel above waits for L1/L2 (long_scoreboard 4.4 stalls per issue): every warp loads the same 43 words
+// per joint for itself.  Here the WARPS warps of a CTA (one tile, adjacent columns) share ONE copy of each joint's
+// 8 KB scratch block ([word][lane], contiguous), which a single thread requests STAGES - 1 joints ahead with
+// cp.async.bulk (global -> shared, completion on an mbarrier); the warps then read shared memory with a fixed latency.
+// One __syncthreads() per joint step hands the consumed buffer back to the producer.  The schedule of a CTA is one
+// linear sequence of joint blocks: main recursion j0..N-1, finishing pass 0..N-1, and for the FD gradient the two
+// passes of the articulated-body solve N-1..0, 0..N-1.  Same arithmetic, same order, same results as the kernel above.
+#ifndef GRID_LPS_BULK
+#define GRID_LPS_BULK 0                // 1: the column kernels of ALG >= 2 use this variant
+#endif
+#ifndef GRID_LPS_BULK_STAGES
+#define GRID_LPS_BULK_STAGES 3
+#endif
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+template <int WARPS, int MODE>
+__global__ void __launch_bounds__(32 * WARPS, 2)
+grad_columns_bulk_kernel(float *__restrict__ d_out, const float *__restrict__ scratch, const float *__restrict__ d_lam,
+                         int num_states, int ntiles, float dt) {
+    constexpr bool SOLVE = MODE == 1 || MODE == 3;
+    constexpr int STAGES = GRID_LPS_BULK_STAGES, JB = W * 32;          // floats per joint block (8 KB)
+    constexpr int cgroups = (2 * N + WARPS - 1) / WARPS;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long full[STAGES];
+    float *buf = smem;                                                  // STAGES joint blocks
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *sa = smem + STAGES * JB + warp * (N * PITCH);
+    int blk = blockIdx.x, sub = 0, sub_tiles = min(kSubTiles, ntiles);
+    while (blk >= cgroups * sub_tiles) {
+        blk -= cgroups * sub_tiles;
+        sub++;
+        sub_tiles = min(kSubTiles, ntiles - sub * kSubTiles);
+    }
+    const int tile = sub * kSubTiles + blk % sub_tiles, cg = blk / sub_tiles;
+    const int cc = cg * WARPS + warp;
+    const bool active = cc < 2 * N;                                     // a CTA past the last column pair idles its spare warps
+    const int j = active ? cc >> 1 : N - 1, side = cc & 1;
+    const int j0 = (cg * WARPS) >> 1;                                   // first joint any warp of this CTA starts at
+    const int cnt = min(32, num_states - tile * 32);
+    const float *tile_base = scratch + (size_t)tile * (N * W * 32);
+    // schedule: [0, nA) main j0..N-1 | [nA, nA+N) finishing 0..N-1 | solve backward N-1..0 | solve forward 0..N-1
+    const int nA = N - j0, T = nA + N + (SOLVE ? 2 * N : 0);
+    auto joint_of = [&](int st) { return st < nA ? j0 + st : st < nA + N ? st - nA : st < nA + 2 * N ? nA + 2 * N - 1 - st : st - nA - 2 * N; };
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < STAGES; b++) mbar_init(&full[b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int st = 0; st < STAGES - 1 && st < T; st++) {
+            mbar_expect_tx(&full[st], JB * 4);
+            bulk_g2s(buf + st * JB, tile_base + (size_t)joint_of(st) * JB, JB * 4, &full[st]);
+        }
+    float dv[6], da[6], P[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, T2[6], F[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, g = 0.f;
+    for (int st = 0; st < T; st++) {
+        __syncthreads();                                                // everyone is done with the buffer of step st - 1
+        if (threadIdx.x == 0 && st + STAGES - 1 < T) {
+            const int b = (st + STAGES - 1) % STAGES;
+            mbar_expect_tx(&full[b], JB * 4);
+            bulk_g2s(buf + b * JB, tile_base + (size_t)joint_of(st + STAGES - 1) * JB, JB * 4, &full[b]);
+        }
+        mbar_wait(&full[st % STAGES], (st / STAGES) & 1);
+        const float *sj = buf + (st % STAGES) * JB + lane;              // this joint's block, [word][lane]
+        const int i = joint_of(st), k = wt_S[i];
+        if (!active) continue;
+        if (st < nA) {                                                  // ---- main recursion
+            if (i < j) continue;
+            float v[6], iv[6], t[6];
+            ld6(sj + 32 * wV, v);
+            ld6(sj + 32 * wIV, iv);
+            const float qd = sj[32 * wQD];
+            if (i == j) {
+                if (side == 0) {
+                    mxS(k, v, dv);
+                    float mxa[6], mf[6];
+                    ld6(sj + 32 * wMXA, mxa);
+                    mxS(k, dv, t);
+#pragma unroll
+                    for (int r = 0; r < 6; r++) da[r] = fmaf(t[r], qd, mxa[r]);
+                    ld6(sj + 32 * wMF, mf);                              // leaves the column at joint j (rows i < j)
+                    const Xf X0 = ldX(sj + 32 * wE0);
+                    xtforce(X0, mf, T2);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 6; r++) { dv[r] = 0.f; T2[r] = 0.f; }
+                    add_at(dv, k, 1.0f);
+                    mxS(k, v, da);
+                }
+            } else {
+                const Xf X = ldX(sj + 32 * wE);
+                float n6[6];
+                xmotion(X, dv, n6);
+#pragma unroll
+                for (int r = 0; r < 6; r++) dv[r] = n6[r];
+                xmotion(X, da, n6);
+                mxS(k, dv, t);
+#pragma unroll
+                for (int r = 0; r < 6; r++) da[r] = fmaf(t[r], qd, n6[r]);
+            }
+            float df[6], idv[6], s0[6];
+            imul(i, da, df);
+            crossf(dv, iv, t);
+#pragma unroll
+            for (int r = 0; r < 6; r++) df[r] += t[r];
+            imul(i, dv, idv);
+            crossf(v, idv, t);
+#pragma unroll
+            for (int r = 0; r < 6; r++) df[r] += t[r];
+            ld6(sj + 32 * wS0, s0);
+            sa[i * PITCH + lane] = dot6(s0, P);
+            const Xf X0 = ldX(sj + 32 * wE0);
+            xtforce(X0, df, t);
+#pragma unroll
+            for (int r = 0; r < 6; r++) P[r] += t[r];
+            if (i == N - 1) {                                            // Total is known: T2 = Total - [dq] mxS(f_j) in the base frame
+#pragma unroll
+                for (int r = 0; r < 6; r++) T2[r] = P[r] - T2[r];
+            }
+        } else if (st < nA + N) {                                       // ---- finishing pass: rows of the column
+            float s0[6];
+            ld6(sj + 32 * wS0, s0);
+            float dc = i < j ? dot6(s0, T2) : dot6(s0, P) - sa[i * PITCH + lane];
+            if (side == 1 && i == j) dc += wt_damping[i];
+            sa[i * PITCH + lane] = dc;
+            if (MODE == 2) g = fmaf(dc, sj[32 * wY], g);
+        } else if (st < nA + 2 * N) {                                   // ---- solve, backward
+            const float y = sj[32 * wDINV] * (sa[i * PITCH + lane] - pick(F, k));
+            sa[i * PITCH + lane] = y;
+            if (i > 0) {
+                float U[6], t[6];
+                ld6(sj + 32 * wU, U);
+#pragma unroll
+                for (int r = 0; r < 6; r++) t[r] = fmaf(U[r], y, F[r]);
+                const Xf X = ldX(sj + 32 * wE);
+                xtforce(X, t, F);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 6; r++) F[r] = 0.f;                  // F becomes the forward accumulator
+            }
+        } else {                                                        // ---- solve, forward
+            float x = sa[i * PITCH + lane];
+            if (i > 0) {
+                float U[6], t[6];
+                ld6(sj + 32 * wU, U);
+                const Xf X = ldX(sj + 32 * wE);
+                xmotion(X, F, t);
+#pragma unroll
+                for (int r = 0; r < 6; r++) F[r] = t[r];
+                x -= sj[32 * wDINV] * dot6(U, F);
+            }
+            add_at(F, k, x);
+            sa[i * PITCH + lane] = MODE == 3 ? fmaf(-dt, x, (side == 1 && i == j) ? 1.0f : 0.0f) : -x;
+        }
+    }
+    if (!active) return;
+    if (MODE == 2) {
+        if (lane < cnt) {
+            const long long stt = (long long)tile * 32 + lane;
+            const float lq = __ldg(d_lam + stt * 2 * N + j);
+            float *o = d_out + stt * 5 * N;
+            if (side == 0) o[2 * N + j] = fmaf(-dt, g, lq);
+            else o[3 * N + j] = __ldg(d_lam + stt * 2 * N + N + j) + dt * (lq - g);
+        }
+    } else if (MODE == 3) {
+        constexpr long long OUTW = 2 * N + 3 * N * N;
+        store_rows(d_out + (long long)tile * 32 * OUTW, OUTW, 2 * N + side * N * N + j * N, sa, N, cnt, lane);
+    } else {
+        store_rows(d_out + (long long)tile * 32 * 2 * N * N, (long long)2 * N * N, side * N * N + j * N, sa, N, cnt, lane);
+    }
+}
+
 // ---- df_du = -Minv dc_du with a caller-supplied Minv (USE_QDD_MINV_FLAG overload) -------------------------------
 // The reference's overload takes qdd and Minv from the caller (algorithms/_forward_dynamics_gradient.py:22-25,
 // 202-220) and must use THAT Minv, so the O(n) solve of the column kernel does not apply: this is the one place
@@ -773,10 +967,16 @@ cudaError_t lps_launch(float *d_out, const float *d_in, int stride, const float 
     auto prod_kern = minv_product_kernel<N>;
     if (PRE && !d_Minv) return cudaErrorInvalidValue;
     auto minv_kern = minv_columns_kernel<kColWarps, ALG == 5>;
+#if GRID_LPS_BULK
+    auto grad_kern = grad_columns_bulk_kernel<kColWarps, GMODE>;
+    constexpr size_t grad_smem = col_smem + sizeof(float) * GRID_LPS_BULK_STAGES * W * 32;
+#else
     auto grad_kern = grad_columns_kernel<kColWarps, GMODE>;
+    constexpr size_t grad_smem = col_smem;
+#endif
     cudaError_t e = cudaSuccess;
     if (ALG == 0 || ALG == 5) e = opt_in_smem((const void *)minv_kern, col_smem);
-    if (e == cudaSuccess && ALG >= 2) e = opt_in_smem((const void *)grad_kern, col_smem);
+    if (e == cudaSuccess && ALG >= 2) e = opt_in_smem((const void *)grad_kern, grad_smem);
     if (e == cudaSuccess && PRE) e = opt_in_smem((const void *)prod_kern, prod_smem);
     if (e != cudaSuccess) return e;
     const int chunk = num_states < kChunkStates ? num_states : kChunkStates;
@@ -803,7 +1003,7 @@ cudaError_t lps_launch(float *d_out, const float *d_in, int stride, const float 
         }
         if (ALG >= 2) {
             const long long blocks = (long long)((2 * N + kColWarps - 1) / kColWarps) * ntiles;
-            grad_kern<<<(unsigned)blocks, 32 * kColWarps, col_smem, stream>>>(out, scratch, qdd, n, ntiles, dt);
+            grad_kern<<<(unsigned)blocks, 32 * kColWarps, grad_smem, stream>>>(out, scratch, qdd, n, ntiles, dt);
             g_kernel_launches.fetch_add(1);
             if (PRE && (e = cudaGetLastError()) == cudaSuccess) {
                 int dev = 0, sms = 148;

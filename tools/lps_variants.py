@@ -13,15 +13,16 @@ from gridcodegenerator_b200 import load_named_robot                     # noqa: 
 from gridcodegenerator_b200.build import build_robot_library            # noqa: E402
 from gridcodegenerator_b200.codegen import KernelPlan                   # noqa: E402
 
-VARIANTS = {"p0_b3": (0, 3), "p0_b2": (0, 2), "p1_b3": (1, 3), "p1_b2": (1, 2), "p2_b2": (2, 2), "p2_b1": (2, 1)}
+VARIANTS = {"p0_b3": (0, 3), "bulk_s2": ("bulk", 2), "bulk_s3": ("bulk", 3), "bulk_s4": ("bulk", 4)}
 
 
 def _build(name):
     robot = load_named_robot("chain64")
     pipe, minb = VARIANTS[name]
     plan = KernelPlan(robot, only_algs=("fd_grad", "id_grad"))
-    so, info = build_robot_library(robot, plan, tag="_y" + name,
-                                   extra_flags=["-DGRID_LPS_PIPELINE=%d" % pipe, "-DGRID_LPS_MINB=%d" % minb])
+    flags = (["-DGRID_LPS_BULK=1", "-DGRID_LPS_BULK_STAGES=%d" % minb] if pipe == "bulk" else
+             ["-DGRID_LPS_PIPELINE=%d" % pipe, "-DGRID_LPS_MINB=%d" % minb])
+    so, info = build_robot_library(robot, plan, tag="_y" + name, extra_flags=flags)
     regs = [l.strip() for l in info.get("ptxas", "").splitlines() if "grad_columns_kernel" in l or "Used" in l]
     out = []
     for i, l in enumerate(regs):
@@ -29,7 +30,7 @@ def _build(name):
             pass
     import re
     txt = info.get("ptxas", "")
-    found = re.findall(r"grad_columns_kernelILi8ELi(\d).*?\n.*?\n.*?Used (\d+) registers", txt)
+    found = re.findall(r"grad_columns(?:_bulk)?_kernelILi8ELi(\d).*?\n.*?\n.*?Used (\d+) registers", txt)
     return name, found
 
 
