@@ -8,6 +8,7 @@ hash of the static csrc/ and include/ files, so a stale library is never loaded.
 from __future__ import annotations
 
 import hashlib
+import json
 import os
 import shutil
 import subprocess
@@ -99,6 +100,8 @@ def build_robot_library(robot: Robot, plan: Optional[KernelPlan] = None, force: 
     info = {"stats": stats, "codegen_s": t1 - t0, "nvcc_s": time.time() - t1, "ptxas": proc.stderr}
     with open(so[:-3] + ".ptxas.txt", "w") as f:
         f.write(proc.stderr)
+    with open(so[:-3] + ".stats.json", "w") as f:
+        json.dump(stats, f)
     if verbose:
         print(proc.stderr)
     return so, info

@@ -525,7 +525,7 @@ class KernelPlan:
                  pipe_warps: int = 8, pipe_sync_every: int = 256, pipe_scratch_lead: int = 160,
                  wps_tc_matmul: bool = False, only_algs=None, pipe_small_states: int = 24576,
                  pipe_small_group_flops: int = 4000, lps_min_states: int = 256, lps_force: bool = False,
-                 tps_half: bool = False):
+                 tps_half: bool = False, pipe_x2: bool = False):
         # every constructor argument except the robot: build.py hashes this into the library name, so
         # a library built with one plan is never returned for another
         self._args = {k: v for k, v in locals().items() if k not in ("self", "robot")}
@@ -566,6 +566,9 @@ class KernelPlan:
         self.pipe_warps = pipe_warps
         self.pipe_sync_every = pipe_sync_every
         self.pipe_scratch_lead = pipe_scratch_lead
+        # stage-1 (column) programs of the two-stage variants with two states per lane on the packed FP32
+        # instructions (pipeline.emit_task x2)
+        self.pipe_x2 = pipe_x2 if isinstance(pipe_x2, dict) else bool(pipe_x2)
         self.pipe: Dict[str, "PipeVariant"] = {}
         if pipe_algs is None:
             # a forest of several trees: one thread per (state, tree) beats one thread per state
@@ -750,7 +753,7 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
         from .pipeline import emit_pipe_struct
         for v, pv in list(plan.pipe.items()) + ([("fd_grad_small", plan.pipe_small)] if plan.pipe_small else []):
             txt, summ = emit_pipe_struct(pv, plan.pipe_min_blocks, plan.pipe_warps, plan.pipe_sync_every,
-                                         plan.pipe_scratch_lead)
+                                         plan.pipe_scratch_lead, x2=plan.pipe_x2)
             out.append(txt)
             stats["pipe_" + v] = summ
     out.append("}}  // namespace GRID_NS::gen\n")

@@ -82,6 +82,10 @@ int grid_set_option(const char *key, const char *value) {
         o.pipe_chunk = unset ? -1 : atoi(value) / 32 * 32;
     } else if (!strcmp(key, "GRID_PIPE_WARPS")) {
         o.pipe_warps = unset ? 0 : atoi(value);
+    } else if (!strcmp(key, "GRID_PIPE_ORDER_CHUNK")) {
+        o.pipe_order_chunk = unset ? -1 : atoi(value);
+    } else if (!strcmp(key, "GRID_PIPE_ONLY_TASK")) {
+        o.pipe_only_task = unset ? -1 : atoi(value);
     } else if (!strcmp(key, "GRID_PIPE_STAGGER_NS")) {
         o.pipe_stagger_ns = unset ? 0 : atoi(value);
     } else {

@@ -28,6 +28,9 @@ static std::atomic<long long> g_calls{0};
 // Scratch words are written and read inside one kernel (by different SMs) in the fused kernel, so
 // they must not go through the non-coherent path: ld.global.cg reads them at L2.
 __device__ __forceinline__ float ldsc(const float *p) { return __ldcg(p); }
+// two-states-per-lane programs (P::X2): the lane's two consecutive states of a 64-state scratch row in one load
+__device__ __forceinline__ float2 ldsc2(const float *p) { return __ldcg(reinterpret_cast<const float2 *>(p)); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }   // folds into an operand modifier
 __device__ __forceinline__ int ld_acquire(const int *p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -132,9 +135,12 @@ template <class P, int STAGE>
 __global__ void __launch_bounds__(32 * P::WARPS, STAGE == 0 ? P::MINB0 : P::MINB1)
 pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0, const float *__restrict__ d_in1,
             float *__restrict__ scratch, unsigned int *__restrict__ ticket, int num_states, int ntiles, int nblk,
-            float gravity, float dt, const float *__restrict__ d_in2, int stagger_ns) {
+            float gravity, float dt, const float *__restrict__ d_in2, int stagger_ns, int task0, int ntasks, int order_blk) {
     using S = PipeShape<P>;
-    constexpr int NTASKS = STAGE == 0 ? P::NTASKS0 : P::NTASKS1;
+    // states per tile: a stage-1 warp of a P::X2 variant runs 64 states (two per lane, packed FP32 instructions);
+    // `ntiles` counts tiles of that size.  Scratch rows then hold 64 states: [tile of 64][word][64].
+    constexpr int SPT = (STAGE == 1 && P::X2) ? 64 : 32;
+    constexpr int SC_ROW = P::X2 ? 64 : 32;
     // experiment (GRID_PIPE_STAGGER_NS): CTAs are placed round-robin over the SMs, so CTAs b, b + #SMs, ... share an
     // SM; starting them apart de-phases their instruction streams
     if (stagger_ns > 0) {
@@ -168,16 +174,41 @@ pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stri
         } else {
             item = blockIdx.x + iter * gridDim.x;
         }
-        if (item >= NTASKS * nblk) break;
-        const int task = item / nblk, blk = item - task * nblk;
+        if (item >= ntasks * nblk) break;
+        int t_rel, blk;
+        if (order_blk > 0) {
+            // chunk-major order (stage 1): all tasks of a chunk of order_blk tile blocks before the next chunk, so that
+            // a scratch line read by several column programs comes from DRAM once and from L2 afterwards; chunks in
+            // DESCENDING order - the end of the batch is what stage 0 wrote last and is still in L2.  The (shorter)
+            // last chunk goes first.
+            const int nch = (nblk + order_blk - 1) / order_blk;
+            const int nb_last = nblk - (nch - 1) * order_blk;
+            int ch, nb, r = item;
+            if (r < ntasks * nb_last) {
+                ch = nch - 1;
+                nb = nb_last;
+            } else {
+                r -= ntasks * nb_last;
+                const int per = ntasks * order_blk;
+                ch = nch - 2 - r / per;
+                r -= (r / per) * per;
+                nb = order_blk;
+            }
+            t_rel = r / nb;
+            blk = ch * order_blk + (r - t_rel * nb);
+        } else {
+            t_rel = item / nblk;
+            blk = item - t_rel * nblk;
+        }
+        const int task = task0 + t_rel;
         // The task programs contain CTA-wide barriers (they keep the warps of the CTA on the same
         // lines of the program), so a warp past the last tile cannot sit out: it recomputes the
         // last tile and stores nothing (its scratch writes duplicate the owner's values).
         const int my_tile = blk * (int)(blockDim.x >> 5) + warp;
         const bool owner = my_tile < ntiles;
         const int tile = owner ? my_tile : ntiles - 1;
-        const long long first = (long long)tile * 32;
-        const int cnt = min(32, num_states - (int)first);
+        const long long first = (long long)tile * SPT;
+        const int cnt = min(SPT, num_states - (int)first);
         if (STAGE == 0) {
             const float *src0 = d_in0 + first * (long long)stride0;
             if (S::IN_LINEAR && stride0 == P::IN0 && aligned16(src0)) {
@@ -191,11 +222,33 @@ pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stri
         // lanes past the end of a ragged tile recompute the last valid state; their scratch lane is
         // private (scratch is allocated in whole tiles) and the flushes only write cnt states
         const int src = min(lane, cnt - 1);
-        float *sc = scratch + (long long)tile * (P::SCRATCH_WORDS * 32) + lane;
         // third input (the caller's Minv of the USE_QDD_MINV_FLAG overload): read by the lane straight from global
         const float *g2 = P::IN2 > 0 ? d_in2 + (first + src) * (long long)P::IN2 : nullptr;
-        P::template run<STAGE>(task, smem + src * S::IN_PAD, sc, sc, s_warp + lane * P::STAGE_PAD,
-                               d_out + first * P::OUT, owner ? cnt : 0, lane, s_warp, gravity, dt, g2);
+        // the lane's scratch column: state (first + lane) of a 32-state tile; garbage in the columns of states past
+        // the end is computed on and never stored
+        float *sc_row = scratch + (first / SC_ROW) * (long long)(P::SCRATCH_WORDS * SC_ROW) + (first % SC_ROW);
+        if (SPT == 64) {
+            if ((P::X2_MASK >> task) & 1ull) {
+                // packed program: states first + 2 lane and first + 2 lane + 1
+                P::template run<STAGE>(task, smem, sc_row + 2 * lane, sc_row, s_warp + lane * P::STAGE_PAD,
+                                       d_out + first * P::OUT, owner ? cnt : 0, lane, s_warp, gravity, dt, g2);
+            } else {
+                // scalar program on a 64-state tile: two halves (every warp of the CTA runs the same task, so the
+                // barriers inside the programs stay matched)
+#pragma unroll 1
+                for (int h = 0; h < 2; h++) {
+                    const int cnt_h = max(0, min(32, cnt - 32 * h));
+                    P::template run<STAGE>(task, smem, sc_row + 32 * h + lane, sc_row, s_warp + lane * P::STAGE_PAD,
+                                           d_out + (first + 32 * h) * P::OUT, owner ? cnt_h : 0, lane, s_warp, gravity,
+                                           dt, g2);
+                    __syncwarp();
+                }
+            }
+        } else {
+            float *sc = sc_row + lane;
+            P::template run<STAGE>(task, smem + src * S::IN_PAD, sc, sc, s_warp + lane * P::STAGE_PAD,
+                                   d_out + first * P::OUT, owner ? cnt : 0, lane, s_warp, gravity, dt, g2);
+        }
         __syncwarp();
     }
 }
@@ -208,8 +261,15 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
                               unsigned int *ticket, int num_states, float gravity, cudaStream_t stream, float dt,
                               const float *d_in2) {
     using S = PipeShape<P>;
-    constexpr int ntasks = STAGE == 0 ? P::NTASKS0 : P::NTASKS1;
-    if (ntasks == 0) return cudaSuccess;
+    constexpr int ntasks_all = STAGE == 0 ? P::NTASKS0 : P::NTASKS1;
+    if (ntasks_all == 0) return cudaSuccess;
+    // profiling (GRID_PIPE_ONLY_TASK = 100 * stage + task): only that task program runs, the other stage is skipped
+    int task0 = 0, ntasks = ntasks_all;
+    if (const int only = options().pipe_only_task; only >= 0) {
+        if (only / 100 != STAGE || only % 100 >= ntasks_all) return cudaSuccess;
+        task0 = only % 100;
+        ntasks = 1;
+    }
     auto kern = pipe_kernel<P, STAGE>;
     constexpr size_t warp_smem = sizeof(float) * S::smem_words(STAGE);
     // candidate CTA sizes: 1, 2, 4, 8 warps and the size the kernel was compiled for
@@ -239,7 +299,8 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
         if (per_sm[NOPT - 1] < 1 && per_sm[0] < 1) return cudaErrorLaunchOutOfResources;
         sms = n;
     }
-    const int ntiles = (num_states + 31) / 32;
+    constexpr int spt = (STAGE == 1 && P::X2) ? 64 : 32;
+    const int ntiles = (num_states + spt - 1) / spt;
     // largest CTA whose items still give every resident CTA slot at least two items, else the smallest
     int wi = -1;
     for (int i = NOPT - 1; i >= 0; i--) {
@@ -258,9 +319,15 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
     const long long items = (long long)ntasks * nblk;
     const long long cap = (long long)sms * per_sm[wi];
     const int blocks = (int)(items < cap ? items : cap);
+    // stage 1 of a two-stage variant: chunk-major item order when the batch is several chunks long
+    int order_blk = 0;
+    if (STAGE == 1 && P::SCRATCH_WORDS > 0 && ntasks > 1) {
+        const int oc = options().pipe_order_chunk >= 0 ? options().pipe_order_chunk : P::ORDER_CHUNK_STATES;
+        if (oc > 0 && num_states >= 2 * oc) order_blk = (oc / spt + w - 1) / w;
+    }
     kern<<<blocks, 32 * w, warp_smem * w, stream>>>(d_out, d_in0, stride0, d_in1, scratch,
                                                     items > cap ? ticket : nullptr, num_states, ntiles, nblk, gravity,
-                                                    dt, d_in2, options().pipe_stagger_ns);
+                                                    dt, d_in2, options().pipe_stagger_ns, task0, ntasks, order_blk);
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -423,11 +490,14 @@ cudaError_t pipe_launch(float *d_out, const float *d_in0, int stride0, const flo
     // it) but measured SLOWER than the staged kernels on every robot (Atlas FD gradient 975 vs 760 us,
     // HyQ 56 vs 43 us, profiles/r1_pipe_fused_vs_staged.md): SMs of one GPC running different programs
     // lose the sharing of the instruction stream in the GPC-level cache.
-    const bool fused = options().pipe_fused != 0;
-    if (fused && P::NT > 1) {
-        bool handled = false;
-        e = pipe_fused_launch<P>(d_out, d_in0, stride0, d_in1, num_states, gravity, stream, handled, dt, d_in2);
-        if (handled || e != cudaSuccess) return e;
+    // (not instantiated for P::X2 variants: their stage-1 programs take 64-state tiles)
+    if constexpr (!P::X2) {
+        const bool fused = options().pipe_fused != 0;
+        if (fused && P::NT > 1) {
+            bool handled = false;
+            e = pipe_fused_launch<P>(d_out, d_in0, stride0, d_in1, num_states, gravity, stream, handled, dt, d_in2);
+            if (handled || e != cudaSuccess) return e;
+        }
     }
     // Two-stage variants can run in chunks of P::CHUNK_STATES states (a multiple of 32; GRID_PIPE_CHUNK
     // overrides; 0 = one chunk, the default): the scratch words of a chunk would then still be in L2
@@ -436,7 +506,7 @@ cudaError_t pipe_launch(float *d_out, const float *d_in0, int stride0, const flo
     // means less re-execution of a program while it is in the instruction caches.
     int chunk = num_states;
     const int chunk_cfg = options().pipe_chunk >= 0 ? options().pipe_chunk : P::CHUNK_STATES;
-    if (P::SCRATCH_WORDS > 0 && chunk_cfg > 0 && chunk_cfg < num_states) chunk = chunk_cfg;
+    if (P::SCRATCH_WORDS > 0 && chunk_cfg > 0 && chunk_cfg < num_states) chunk = (chunk_cfg + 63) / 64 * 64;
     const int nchunks = (num_states + chunk - 1) / chunk;
     // one allocation: [ticket counters: 2 per chunk, padded to 256 B | scratch words of one chunk];
     // small batches need no tickets, single-stage variants no scratch
@@ -452,7 +522,8 @@ cudaError_t pipe_launch(float *d_out, const float *d_in0, int stride0, const flo
     // every item has its own CTA)
     const bool use_tickets = max_items > 4LL * sms;
     const size_t tk_bytes = use_tickets ? ((size_t)nchunks * 2 * sizeof(unsigned int) + 255) / 256 * 256 : 0;
-    const size_t sc_bytes = (size_t)((chunk + 31) / 32) * P::SCRATCH_WORDS * 32 * sizeof(float);
+    constexpr int sc_row = P::X2 ? 64 : 32;
+    const size_t sc_bytes = (size_t)((chunk + sc_row - 1) / sc_row) * P::SCRATCH_WORDS * sc_row * sizeof(float);
     unsigned int *tickets = nullptr;
     float *sc = nullptr;
     e = cudaSuccess;

@@ -24,6 +24,8 @@ struct Options {
     int pipe_chunk;         // states per chunk of a two-stage launch; -1 = the compiled default
     int pipe_warps;         // warps per CTA of the phase-split kernels; 0 = chosen from the batch size
     int pipe_stagger_ns;    // experiment: CTAs that share an SM start this many ns apart (de-phased instruction streams)
+    int pipe_order_chunk;   // stage-1 items ordered chunk-major: states per chunk (0 = task-major over the whole batch; -1 = default)
+    int pipe_only_task;     // profiling: 100 * stage + task = launch only that task program (results incomplete); -1 = all
 };
 inline int parse_force(const char *f) {
     if (!f || !*f) return kAuto;
@@ -47,6 +49,10 @@ inline Options &options() {
         x.pipe_warps = w ? atoi(w) : 0;
         const char *st = getenv("GRID_PIPE_STAGGER_NS");
         x.pipe_stagger_ns = st ? atoi(st) : 0;
+        const char *oc = getenv("GRID_PIPE_ORDER_CHUNK");
+        x.pipe_order_chunk = oc ? atoi(oc) : -1;
+        const char *ot = getenv("GRID_PIPE_ONLY_TASK");
+        x.pipe_only_task = ot ? atoi(ot) : -1;
         return x;
     }();
     return o;

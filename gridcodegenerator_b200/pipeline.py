@@ -90,6 +90,12 @@ class PipeTask:
         self.counts = program.op_counts()
         self.cost = self.counts["nodes"]              # refined by emit_task (instructions, incl. loads and flushes)
 
+    def program_reads_only_scratch(self) -> bool:
+        p = self.program
+        live = p.live_nodes()
+        return all(k[1] in ("gravity", "dt") or k[1].startswith("sc:")
+                   for i, k in enumerate(p.nodes) if live[i] and k[0] == "in")
+
     @property
     def flops(self) -> int:
         return self.counts["flops"]
@@ -473,7 +479,8 @@ class PipeVariant:
 
     def summary(self) -> Dict[str, object]:
         return {"flops": self.flops, "scratch_words": self.scratch_words,
-                "tasks": [(t.name, t.stage, t.flops, getattr(t, "instr", 0)) for st in self.stage_tasks for t in st]}
+                "tasks": [(t.name, t.stage, t.flops, getattr(t, "instr", 0)) for st in self.stage_tasks for t in st],
+                "x2_live": [getattr(t, "x2_live", None) for t in self.stage_tasks[1]]}
 
 
 # ---- emission ----------------------------------------------------------------------------------
@@ -485,10 +492,19 @@ def _flit(x: float) -> str:
 
 
 def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead: int = 24,
-              scratch_lead: int = 160, indent: str = "        ", sync_every: int = 0) -> List[str]:
+              scratch_lead: int = 160, indent: str = "        ", sync_every: int = 0, x2: bool = False,
+              sc_stride: int = 32, remat_gap: int = 0) -> List[str]:
     """One task as a __device__ function.  Input loads are issued `lead` operations before
     their first use (long enough to cover the L2 latency of scratch reads, short enough not to
-    pin registers); output runs are flushed as soon as their last value exists."""
+    pin registers); output runs are flushed as soon as their last value exists.
+
+    x2: the lane runs the program for TWO consecutive states at once, every value a float2 computed with the
+    sm_100 packed FP32 instructions (FFMA2 / FMUL2 / FADD2: literals ride as a broadcast immediate, negations as
+    operand modifiers) - half the instructions per state for kernels that are bound by instruction supply.  Only
+    programs whose inputs are scratch words (stage 1).  sc_stride: states per scratch word row (64 when the
+    consumers are x2 programs)."""
+    if x2:
+        return _emit_task_x2(t, fname, out_words, stage_pad, scratch_lead, indent, sync_every, remat_gap)
     p = t.program
     live = p.live_nodes()
     sc_word = getattr(t, "sc_word", {})
@@ -514,7 +530,7 @@ def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead
         elif name.startswith("g2:"):
             stmt, lead = "const float t%d = __ldg(g_in2 + %d);" % (o, int(name[3:])), scratch_lead
         else:
-            stmt, lead = "const float t%d = pipe::ldsc(sc_in + %d);" % (o, 32 * sc_word[name]), scratch_lead
+            stmt, lead = "const float t%d = pipe::ldsc(sc_in + %d);" % (o, sc_stride * sc_word[name]), scratch_lead
         load_pos[o] = max(0, fu - lead)
         loads_at.setdefault(load_pos[o], []).append(indent + stmt)
 
@@ -532,7 +548,7 @@ def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead
         where = -1 if v.is_const else (load_pos[v.i] if p.nodes[v.i][0] == "in" else pos[v.i])
         if name == "sc":
             expr = _flit(v.c) if v.is_const else "%st%d" % ("-" if v.s < 0 else "", v.i)
-            sc_at.setdefault(where, []).append("%ssc_out[%d] = %s;" % (indent, 32 * idx, expr))
+            sc_at.setdefault(where, []).append("%ssc_out[%d] = %s;" % (indent, sc_stride * idx, expr))
         else:
             ri = run_of[idx]
             if idx in run_vals[ri]:
@@ -619,10 +635,245 @@ def emit_task(t: PipeTask, fname: str, out_words: int, stage_pad: int, tile_lead
     return body
 
 
+def x2_clusters(t: PipeTask, remat_gap: int):
+    """Use positions (in emission order) of every live input of the task, clustered: a new cluster starts where two
+    consecutive uses are more than remat_gap operations apart (0 = one cluster).  -> (order, pos, {input: [[pos...]]})"""
+    p = t.program
+    live = p.live_nodes()
+    order = [i for i, k in enumerate(p.nodes) if live[i] and k[0] != "in"]
+    pos = {i: c for c, i in enumerate(order)}
+    use_pos: Dict[int, List[int]] = {}
+    for i in order:
+        for o in p.operands(i):
+            if p.nodes[o][0] == "in":
+                use_pos.setdefault(o, []).append(pos[i])
+    for (name, idx, v) in p.outputs:
+        if not v.is_const and p.nodes[v.i][0] == "in":
+            use_pos.setdefault(v.i, []).insert(0, 0)
+    clusters: Dict[int, List[List[int]]] = {}
+    for o, us in use_pos.items():
+        us = sorted(set(us))
+        cl = [[us[0]]]
+        for u in us[1:]:
+            if remat_gap and u - cl[-1][-1] > remat_gap and p.nodes[o][1].startswith("sc:"):
+                cl.append([u])
+            else:
+                cl[-1].append(u)
+        clusters[o] = cl
+    return order, pos, clusters
+
+
+def x2_max_live(t: PipeTask, scratch_lead: int, remat_gap: int) -> int:
+    """Values alive at once when the task is emitted in program order with its loads `scratch_lead` operations ahead
+    of each cluster of uses: the estimate that decides whether the packed form (two registers per value) fits."""
+    p = t.program
+    order, pos, clusters = x2_clusters(t, remat_gap)
+    last = {}
+    for i in order:
+        for o in p.operands(i):
+            if p.nodes[o][0] != "in":
+                last[o] = pos[i]
+    delta = [0] * (len(order) + 2)
+    for o, b in last.items():
+        delta[pos[o]] += 1
+        delta[b + 1] -= 1
+    for o, cls in clusters.items():
+        for cl in cls:
+            delta[max(0, cl[0] - scratch_lead)] += 1
+            delta[cl[-1] + 1] -= 1
+    cur = best = 0
+    for d in delta:
+        cur += d
+        best = max(best, cur)
+    return best
+
+
+def _emit_task_x2(t: PipeTask, fname: str, out_words: int, stage_pad: int, scratch_lead: int, indent: str,
+                  sync_every: int, remat_gap: int = 0) -> List[str]:
+    """The two-states-per-lane (float2) form of emit_task; see there.  The scratch rows hold 64 states, the lane
+    reads words 2*lane, 2*lane+1 with one 64-bit load.  nvcc does not contract the packed intrinsics, so a product
+    whose only use is a sum is fused into FFMA2 here.  Output runs go through the warp's 32 staging rows twice:
+    first the even states of the 64-state tile (.x), then the odd ones (.y).
+
+    remat_gap > 0: a scratch word whose uses lie more than remat_gap operations apart is loaded again for each
+    cluster of uses instead of occupying a register pair in between (M^-1 entries are used by every column of a
+    group; packed values cost two registers each and the programs were sized for 255 scalar registers)."""
+    p = t.program
+    live = p.live_nodes()
+    sc_word = getattr(t, "sc_word", {})
+    order, pos, clusters = x2_clusters(t, remat_gap)
+    uses = [0] * len(p.nodes)
+    for i in order:
+        for o in p.operands(i):
+            uses[o] += 1
+    for (name, idx, v) in p.outputs:
+        if not v.is_const:
+            uses[v.i] += 1
+    # product -> the sum that absorbs it
+    fused_into: Dict[int, int] = {}
+    for i in order:
+        k = p.nodes[i]
+        if k[0] == "add":
+            for cand in (k[2], k[1]):
+                if p.nodes[cand][0] in ("mul", "mulc") and uses[cand] == 1 and cand not in fused_into and live[cand]:
+                    fused_into[cand] = i
+                    break
+    loads_at: Dict[int, List[str]] = {}
+    load_pos: Dict[int, int] = {}
+    n_loads = 0
+    for o, cls in clusters.items():
+        name = p.nodes[o][1]
+        for ci, cl in enumerate(cls):
+            var = "t%d" % o if ci == 0 else "t%dr%d" % (o, ci)
+            if name in ("gravity", "dt"):
+                stmt, lead = "const float2 %s = make_float2(%s, %s);" % (var, name, name), 0
+            elif name.startswith("sc:"):
+                stmt, lead = "const float2 %s = pipe::ldsc2(sc_in + %d);" % (var, 64 * sc_word[name]), scratch_lead
+            else:
+                raise ValueError("x2 task %s reads %r: only scratch words and scalars are supported" % (t.name, name))
+            at = max(0, cl[0] - lead)
+            if ci == 0:
+                load_pos[o] = at
+            loads_at.setdefault(at, []).append(indent + stmt)
+            n_loads += 1
+    cur = [0]
+
+    def nm(o: int) -> str:
+        """name of node o at the current position (inputs: the cluster that covers it)"""
+        cls = clusters.get(o)
+        if not cls or len(cls) == 1:
+            return "t%d" % o
+        ci = 0
+        while ci + 1 < len(cls) and cls[ci + 1][0] <= cur[0]:
+            ci += 1
+        return "t%d" % o if ci == 0 else "t%dr%d" % (o, ci)
+
+    run_of: Dict[int, int] = {}
+    for ri, (offs, ln) in enumerate(t.runs):
+        for off in offs:
+            for c in range(ln):
+                run_of[off + c] = ri
+    run_vals: List[Dict[int, V]] = [dict() for _ in t.runs]
+    run_last = [-1] * len(t.runs)
+    for (name, idx, v) in p.outputs:
+        if name == "sc":
+            raise ValueError("x2 task %s writes scratch words" % t.name)
+        where = -1 if v.is_const else (load_pos[v.i] if p.nodes[v.i][0] == "in" else pos[v.i])
+        ri = run_of[idx]
+        if idx in run_vals[ri]:
+            raise ValueError("output word %d written twice" % idx)
+        run_vals[ri][idx] = v
+        run_last[ri] = max(run_last[ri], where)
+    flush_at: Dict[int, List[int]] = {}
+    for ri, (offs, ln) in enumerate(t.runs):
+        if len(run_vals[ri]) != ln * len(offs):
+            raise ValueError("task %s does not cover run %d" % (t.name, ri))
+        flush_at.setdefault(run_last[ri], []).append(ri)
+
+    def flush(ri: int) -> List[str]:
+        offs, ln = t.runs[ri]
+        L = []
+        for h, half in enumerate("xy"):
+            for si, off in enumerate(offs):
+                for c in range(ln):
+                    v = run_vals[ri][off + c]
+                    expr = _flit(v.c) if v.is_const else "%st%d.%s" % ("-" if v.s < 0 else "", v.i, half)
+                    L.append("%ss_stage[%d] = %s;" % (indent, si * ln + c, expr))
+            L.append("%s__syncwarp();" % indent)
+            cnt_h = "(cnt + 1) >> 1" if h == 0 else "cnt >> 1"
+            if len(offs) == 1:
+                L.append("%spipe::flush1<%d, %d, %d>(g_tile + %d, s_warp, %d, %s, lane);" % (
+                    indent, 2 * out_words, ln, stage_pad, h * out_words, offs[0], cnt_h))
+            else:
+                L.append("%spipe::flush2<%d, %d, %d>(g_tile + %d, s_warp, %d, %d, %s, lane);" % (
+                    indent, 2 * out_words, ln, stage_pad, h * out_words, offs[0], offs[1], cnt_h))
+            L.append("%s__syncwarp();" % indent)
+        return L
+
+    def bc(c: float) -> str:
+        f = _flit(c)
+        return "make_float2(%s, %s)" % (f, f)
+
+    def sg(i: int, negate: bool) -> str:
+        return "pipe::neg2(%s)" % nm(i) if negate else nm(i)
+
+    def second(kc, negate: bool) -> str:
+        """second factor of the product node kc, optionally negated"""
+        return sg(kc[2], negate) if kc[0] == "mul" else bc(-kc[2] if negate else kc[2])
+
+    body: List[str] = ["    // %s (two states per lane): %d mul + %d add per state" % (t.name, t.counts["mul"], t.counts["add"]),
+                       "    static __device__ __noinline__ void %s(const float *s_in, const float *__restrict__ sc_in,"
+                       " float *__restrict__ sc_out, float *s_stage, float *__restrict__ g_tile, const int cnt,"
+                       " const int lane, const float *s_warp, const float gravity, const float dt,"
+                       " const float *__restrict__ g_in2) {" % fname,
+                       indent + "__builtin_assume(__isShared(s_stage)); __builtin_assume(__isShared(s_warp));"]
+    for ri in flush_at.get(-1, []):
+        body += flush(ri)
+    for c in range(max(1, len(order))):
+        cur[0] = c
+        if sync_every and c and c % sync_every == 0:
+            body.append(indent + "__syncthreads();")
+        body += loads_at.get(c, [])
+        i = order[c] if c < len(order) else None
+        k = p.nodes[i] if i is not None else ("nop",)
+        op = k[0]
+        if op == "nop" or i in fused_into:
+            pass
+        elif op in ("sin", "cos"):
+            body.append("%sconst float2 t%d = make_float2(%sf(%s.x), %sf(%s.y));" % (indent, i, op, nm(k[1]), op, nm(k[1])))
+        elif op == "rcp":
+            body.append("%sconst float2 t%d = make_float2(1.0f / %s.x, 1.0f / %s.y);" % (indent, i, nm(k[1]), nm(k[1])))
+        elif op in ("mul", "mulc"):
+            body.append("%sconst float2 t%d = __fmul2_rn(%s, %s);" % (indent, i, nm(k[1]), second(k, False)))
+        elif op == "add":
+            a, b, rel = k[1], k[2], k[3]
+            if fused_into.get(b) == i:            # a + rel * (x * y)
+                kc = p.nodes[b]
+                body.append("%sconst float2 t%d = __ffma2_rn(%s, %s, %s);" % (indent, i, nm(kc[1]), second(kc, rel < 0), nm(a)))
+            elif fused_into.get(a) == i:          # (x * y) + rel * b
+                kc = p.nodes[a]
+                body.append("%sconst float2 t%d = __ffma2_rn(%s, %s, %s);" % (indent, i, nm(kc[1]), second(kc, False),
+                                                                            sg(b, rel < 0)))
+            else:
+                body.append("%sconst float2 t%d = __fadd2_rn(%s, %s);" % (indent, i, nm(a), sg(b, rel < 0)))
+        elif op == "addc":
+            body.append("%sconst float2 t%d = __fadd2_rn(%s, %s);" % (indent, i, nm(k[1]), bc(k[2])))
+        else:
+            raise ValueError("pipe emitter: unsupported node %r" % (k,))
+        for ri in flush_at.get(c, []):
+            body += flush(ri)
+    body.append("    }")
+    # per-state instruction estimate (the packed program serves two states)
+    n_instr = len(order) - len(fused_into) + n_loads
+    n_instr += 2 * sum(len(offs) * ln + 48 for (offs, ln) in t.runs)
+    n_instr //= 2
+    t.cost = int(min(n_instr, 4096) + 3.4 * max(0, n_instr - 4096))
+    t.instr = n_instr
+    return body
+
+
 def emit_pipe_struct(pv: PipeVariant, min_blocks: Tuple[int, int] = (1, 1), warps: int = 8,
-                     sync_every: int = 256, scratch_lead: int = 160, chunk_states: int = 0) -> Tuple[str, Dict[str, object]]:
+                     sync_every: int = 256, scratch_lead: int = 160, chunk_states: int = 0,
+                     x2=False, order_chunk_states: int = 0) -> Tuple[str, Dict[str, object]]:
     """min_blocks: resident CTAs per SM the two stage kernels are compiled for (register cap =
-    65536 / (32 * warps * min_blocks)); warps: tiles (warps) per CTA."""
+    65536 / (32 * warps * min_blocks)); warps: tiles (warps) per CTA.
+
+    x2 (False, True or a dict of options): stage-1 programs of a two-stage variant run two states per lane with
+    the packed FP32 instructions (emit_task) when their register demand allows it - at most `max_live` values alive
+    at once (two registers each) with scratch words re-loaded for uses more than `remat_gap` operations apart and
+    loads issued `lead` operations ahead.  Stage-1 warps then take 64-state tiles; the programs that stay scalar run
+    a tile as two halves."""
+    xo = dict(max_live=110, remat_gap=200, lead=80)
+    if isinstance(x2, dict):
+        xo.update(x2)
+    x2 = bool(x2) and pv.scratch_words > 0 and all(t.stage == 0 or t.program_reads_only_scratch() for t in pv.tasks)
+    x2_tasks = set()
+    if x2:
+        for ti, t in enumerate(pv.stage_tasks[1]):
+            t.x2_live = x2_max_live(t, xo["lead"], xo["remat_gap"])
+            if t.x2_live <= xo["max_live"]:
+                x2_tasks.add(ti)
+        x2 = bool(x2_tasks)
     max_run = max([len(offs) * ln for t in pv.tasks for (offs, ln) in t.runs] + [1])
     # row pitch of the staging tile: even (float2 flushes) when every run length is even, else odd
     # (conflict-free scalar access); never a multiple of 32
@@ -637,11 +888,20 @@ def emit_pipe_struct(pv: PipeVariant, min_blocks: Tuple[int, int] = (1, 1), warp
                len(pv.stage_tasks[0]), len(pv.stage_tasks[1]), min_blocks[0], min_blocks[1], warps),
            "    static constexpr long long TRACED_FLOPS = %d;" % pv.flops,
            "    static constexpr int SYNC_EVERY = %d;" % (sync_every if warps > 1 else 0),
-           "    static constexpr int CHUNK_STATES = %d;" % chunk_states]
+           "    static constexpr int CHUNK_STATES = %d;" % chunk_states,
+           "    static constexpr int ORDER_CHUNK_STATES = %d;   // stage-1 item order (grid_pipe.cuh); 0 = task-major" % order_chunk_states,
+           "    // X2 = 1: stage-1 warps take 64-state tiles; bit t of X2_MASK: stage-1 task t is a two-states-per-lane",
+           "    // (packed FP32) program, the others run the tile as two 32-state halves",
+           "    static constexpr int X2 = %d;" % int(x2),
+           "    static constexpr unsigned long long X2_MASK = %dull;" % sum(1 << ti for ti in x2_tasks)]
+    if len(pv.stage_tasks[1]) > 64:
+        raise ValueError("more than 64 stage-1 tasks")
     for s in (0, 1):
         for ti, t in enumerate(pv.stage_tasks[s]):
+            is2 = x2 and s == 1 and ti in x2_tasks
             txt += emit_task(t, "s%d_t%d" % (s, ti), pv.out, stage_pad, sync_every=sync_every if warps > 1 else 0,
-                             scratch_lead=scratch_lead)
+                             scratch_lead=xo["lead"] if is2 else scratch_lead, x2=is2, sc_stride=64 if x2 else 32,
+                             remat_gap=xo["remat_gap"])
     txt.append("    template <int STAGE> static __device__ __forceinline__ void run(const int task, const float *s_in,"
                " const float *__restrict__ sc_in, float *__restrict__ sc_out, float *s_stage,"
                " float *__restrict__ g_tile, const int cnt, const int lane, const float *s_warp, const float gravity,"

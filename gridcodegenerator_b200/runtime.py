@@ -301,7 +301,8 @@ class GridEngine:
 
     # ---- options: the library reads the environment once; later changes of the same variables in
     # THIS process (tests, sweeps) are pushed through grid_set_option before a call -----------------
-    _OPTION_KEYS = ("GRID_FORCE_KERNEL", "GRID_PIPE_MODE", "GRID_PIPE_CHUNK", "GRID_PIPE_WARPS", "GRID_PIPE_STAGGER_NS")
+    _OPTION_KEYS = ("GRID_FORCE_KERNEL", "GRID_PIPE_MODE", "GRID_PIPE_CHUNK", "GRID_PIPE_WARPS", "GRID_PIPE_STAGGER_NS",
+                    "GRID_PIPE_ONLY_TASK", "GRID_PIPE_ORDER_CHUNK")
 
     def _sync_options(self):
         cur = tuple(os.environ.get(k) for k in self._OPTION_KEYS)

@@ -141,8 +141,10 @@ void grid_graph_destroy(grid_graph *g);
 
 /* ---- options ------------------------------------------------------------------------------
  * The environment variables GRID_FORCE_KERNEL (tps|wps|cps|pipe), GRID_PIPE_MODE (staged|fused),
- * GRID_PIPE_CHUNK (states), GRID_PIPE_WARPS (CTA width of the phase-split kernels) and GRID_PIPE_STAGGER_NS
- * (experiment: start offset between CTAs that share an SM) are read ONCE, at the first launch; afterwards they change only through
+ * GRID_PIPE_CHUNK (states), GRID_PIPE_WARPS (CTA width of the phase-split kernels), GRID_PIPE_STAGGER_NS
+ * (experiment: start offset between CTAs that share an SM), GRID_PIPE_ORDER_CHUNK (experiment: stage-1 items in
+ * chunk-major order, states per chunk) and GRID_PIPE_ONLY_TASK (profiling: 100 * stage + task runs that one task
+ * program only - the results are then incomplete) are read ONCE, at the first launch; afterwards they change only through
  * this call (value NULL or "" restores the default).  Nothing on the launch path calls getenv. */
 int grid_set_option(const char *key, const char *value);
 

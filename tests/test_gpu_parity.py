@@ -335,6 +335,40 @@ def test_forced_split_of_single_tree_robots(name, mode, monkeypatch):
         assert np.isfinite(out).all()
 
 
+@pytest.mark.parametrize("N", [1, 31, 33, 63, 64, 65, 1000, 4099])
+def test_packed_two_states_per_lane_column_programs(N, monkeypatch):
+    """KernelPlan(pipe_x2=...): stage-1 warps take 64-state tiles; column programs under the register-demand
+    threshold run two states per lane on FFMA2 / FMUL2 / FADD2 with re-loaded scratch words, the others run the tile
+    as two halves (library variant built by __graft_entry__.build()).  Ragged tiles, guard rows, the oracle."""
+    import __graft_entry__ as G
+    from gridcodegenerator_b200.runtime import GridEngine
+    robot = load_named_robot("iiwa14")
+    n = robot.n
+    eng = GridEngine(robot, plan=G.x2_test_plan(robot), tag=G.X2_TEST_TAG)
+    st = eng.build_info.get("stats", {}).get("pipe_fd_grad")
+    if st:                                       # freshly built here: both kinds of stage-1 programs exist
+        lives = st["x2_live"]
+        assert any(v <= 70 for v in lives) and any(v > 70 for v in lives)
+    monkeypatch.setenv("GRID_FORCE_KERNEL", "pipe")
+    q, qd, u, qdd = make_states(n, N, 77)
+    q64, qd64, u64, qdd64 = (x.astype(np.float64) for x in (q, qd, u, qdd))
+    M = min(N, 128)
+    for alg, kw, ref in (("id_grad", {}, O.batch(robot, "id_grad", q64[-M:], qd64[-M:])),
+                         ("id_grad", dict(qdd=qdd), O.batch(robot, "id_grad", q64[-M:], qd64[-M:], qdd64[-M:])),
+                         ("fd_grad", {}, O.batch(robot, "fd_grad", q64[-M:], qd64[-M:], u64[-M:]))):
+        assert "pipe" in eng.kernel_kind(alg)
+        out = run_alg(eng, alg, q, qd, u, **kw)
+        assert np.isfinite(out).all()
+        assert relerr(out[-M:], ref) < TOL[alg], (alg, N, relerr(out[-M:], ref))
+    # guard rows around a ragged batch
+    guard = torch.full((N + 2, 2 * n * n), 7.0, device="cuda")
+    eng.forward_dynamics_gradient_device(guard[1:N + 1], dev(pack_q_qd_u(q, qd, u)), num_timesteps=N, stride=3 * n)
+    torch.cuda.synchronize()
+    g = guard.cpu().numpy()
+    assert np.all(g[0] == 7.0) and np.all(g[-1] == 7.0)
+    assert np.array_equal(g[1:N + 1], out)
+
+
 @pytest.mark.parametrize("name,N", [("atlas", 1000), ("hyq", 4099)])
 def test_pipe_fused_variant_matches_staged(name, N, monkeypatch):
     """The SM-partitioned single-kernel variant (GRID_PIPE_MODE=fused: stage-1 warps wait on

@@ -44,6 +44,17 @@ VARIANTS = {
     "w1_mb8":    dict(pipe_warps=1, pipe_min_blocks=(8, 8)),
     "lead320":   dict(pipe_scratch_lead=320),
     "lead80":    dict(pipe_scratch_lead=80),
+    # stage-1 programs with two states per lane (FFMA2 / FMUL2 / FADD2)
+    "x2":        dict(pipe_x2=True),
+    "x2_g4000":  dict(pipe_x2=True, pipe_opts=dict(group_flops=4000)),
+    "x2_g3000":  dict(pipe_x2=True, pipe_opts=dict(group_flops=3000)),
+    "x2_s0":     dict(pipe_x2=True, pipe_sync_every=0),
+    # ... only the programs whose register demand allows it (scratch words re-loaded per cluster of uses)
+    "x2m":       dict(pipe_x2=dict(max_live=110, remat_gap=200, lead=80)),
+    "x2m_g4000": dict(pipe_x2=dict(max_live=110, remat_gap=200, lead=80), pipe_opts=dict(group_flops=4000)),
+    "x2m_ml125": dict(pipe_x2=dict(max_live=125, remat_gap=100, lead=40)),
+    "x2m_gap100": dict(pipe_x2=dict(max_live=110, remat_gap=100, lead=40)),
+    "x2m_w4":    dict(pipe_x2=dict(max_live=110, remat_gap=200, lead=80), pipe_warps=4, pipe_min_blocks=(2, 2)),
 }
 
 
@@ -98,6 +109,39 @@ def run(names):
                 us = eng.time_launches(ALG, out, x, num_timesteps=N, stride=3 * n, reps=20 if N > 1000 else 100)
                 res["us_N%d" % N] = float(np.median(us))
             res["evals_per_s_N65536"] = 65536 / res["us_N65536"] * 1e6
+            if os.environ.get("VARIANT_TASKS"):          # per-task times: only that program runs (GRID_PIPE_ONLY_TASK)
+                from gridcodegenerator_b200.build import lib_path
+                sj = lib_path(robot, "_x" + name, plan_for(robot, name))[:-3] + ".stats.json"
+                st = json.load(open(sj)).get("pipe_" + ALG, {}) if os.path.exists(sj) else {}
+                res["tasks"] = st.get("tasks")
+                res["x2_live"] = st.get("x2_live")
+                per = {}
+                for stage, cnt in ((0, 8), (1, 40)):
+                    for k in range(cnt):
+                        eng.set_option("GRID_PIPE_ONLY_TASK", str(100 * stage + k))
+                        us = float(np.median(eng.time_launches(ALG, out, x, num_timesteps=65536, stride=3 * n, reps=5)))
+                        if us < 3.0:
+                            break
+                        per["s%d_t%d" % (stage, k)] = us
+                eng.set_option("GRID_PIPE_ONLY_TASK", None)
+                res["task_us_N65536"] = per
+            if os.environ.get("VARIANT_ORDER"):          # stage-1 item order: chunk-major with chunks of this many states
+                for oc in (0, 8192, 16384, 32768):
+                    eng.set_option("GRID_PIPE_ORDER_CHUNK", str(oc))
+                    for N in (65536, 262144):
+                        if N > NMAX:
+                            continue
+                        us = eng.time_launches(ALG, out, x, num_timesteps=N, stride=3 * n, reps=20)
+                        res["us_N%d_order%d" % (N, oc)] = float(np.median(us))
+                    eng.forward_dynamics_gradient_device(out, x)
+                    torch.cuda.synchronize()
+                    res["relerr_order%d" % oc] = float(np.abs(out[:512].cpu().numpy() - ref).max() / np.abs(ref).max())
+                    chk = out[-4096:].double().sum().item()
+                    res["tail_checksum_order%d" % oc] = chk
+                eng.set_option("GRID_PIPE_ORDER_CHUNK", None)
+            if os.environ.get("VARIANT_QUICK"):
+                print(json.dumps(res), flush=True)
+                continue
             for w in (8, 4, 2):                     # CTA width pinned (GRID_PIPE_WARPS) at the strong-scaling shard size
                 eng.set_option("GRID_PIPE_WARPS", str(w))
                 res["us_N8192_w%d" % w] = float(np.median(eng.time_launches(ALG, out, x, num_timesteps=8192, stride=3 * n, reps=20)))
