@@ -883,6 +883,101 @@ def trace_fd_grad_paired(robot: Robot, use_qdd_minv: bool = False, park: Sequenc
     return p
 
 
+# ---- further algorithms: mass matrix and O(n) forward dynamics ---------------------
+def crba(sr: SymRobot) -> Dict[Tuple[int, int], V]:
+    """Composite-rigid-body algorithm: the joint-space mass matrix M(q) as {(row, col): V}, row <= col (entries between
+    joints of different branches are structural zeros and absent).  The reference has no CRBA; M is pinned to it
+    through its RNEA (column j of M = RNEA(q, 0, e_j) - RNEA(q, 0, 0), tests/golden) and through M Minv = I."""
+    p, robot, n = sr.p, sr.robot, sr.n
+    Ic = [[list(row) for row in sr.I[i]] for i in range(n)]
+    M: Dict[Tuple[int, int], V] = {}
+    # one sweep, leaves first: the composite inertia of joint i is final once its children are done - column i of M
+    # (F = Ic_i S_i carried up the ancestors) is produced right there and Ic_i dies as soon as it is folded into its
+    # parent, so only the open branches hold registers (30 composite inertias kept to a second loop: 5.4 KB of spills
+    # per thread on Atlas)
+    for i in range(n - 1, -1, -1):
+        k, par = robot.S_ind[i], robot.parent[i]
+        F = [Ic[i][r][k] for r in range(6)]
+        M[(i, i)] = F[k]
+        j = i
+        while robot.parent[j] >= 0:
+            F = sr.XT_force(j, F)
+            j = robot.parent[j]
+            M[(j, i)] = F[robot.S_ind[j]]
+        if par >= 0:
+            Ip = sr.congruence(i, Ic[i])
+            Ic[par] = [[Ic[par][r][c] + Ip[r][c] for c in range(6)] for r in range(6)]
+        Ic[i] = None
+    return M
+
+
+def aba(sr: SymRobot, qd: Sequence[V], u: Sequence[V], gravity: V) -> List[V]:
+    """Articulated-body algorithm: qdd = FD(q, qd, u) in O(n), without M^-1.  Same conventions as rnea() above
+    (base acceleration X[:,5] * gravity, joint damping); equals the reference's Minv (u - c) up to rounding."""
+    p, robot, n = sr.p, sr.robot, sr.n
+    v: List[List[V]] = [None] * n
+    cb: List[Optional[List[V]]] = [None] * n
+    pA: List[List[V]] = [None] * n
+    for i in range(n):
+        par, k = robot.parent[i], robot.S_ind[i]
+        v[i] = zeros(p, 6) if par < 0 else sr.X_motion(i, v[par])
+        v[i][k] = v[i][k] + qd[i]
+        cb[i] = cross_motion_axis(p, k, v[i], qd[i]) if par >= 0 else None
+        pA[i] = cross_force(v[i], sr.I_mul(i, v[i]))
+    IA = [[list(row) for row in sr.I[i]] for i in range(n)]
+    U: List[List[V]] = [None] * n
+    Dinv: List[V] = [None] * n
+    uu: List[V] = [None] * n
+    for i in range(n - 1, -1, -1):
+        par, k = robot.parent[i], robot.S_ind[i]
+        U[i] = [IA[i][r][k] for r in range(6)]
+        Dinv[i] = p.rcp(U[i][k])
+        uu[i] = u[i] - qd[i] * robot.damping[i] - pA[i][k]
+        if par >= 0:
+            UD = vscale(U[i], Dinv[i])
+            Ia = [[None] * 6 for _ in range(6)]
+            for r in range(6):
+                for c in range(r, 6):
+                    Ia[r][c] = IA[i][r][c] - UD[r] * U[i][c]
+                    Ia[c][r] = Ia[r][c]
+            pa = vadd(vadd(pA[i], matvec(Ia, cb[i])), vscale(UD, uu[i]))
+            Ip = sr.congruence(i, Ia)
+            IA[par] = [[IA[par][r][c] + Ip[r][c] for c in range(6)] for r in range(6)]
+            pA[par] = vadd(pA[par], sr.XT_force(i, pa))
+    a: List[List[V]] = [None] * n
+    qdd: List[V] = [None] * n
+    for i in range(n):
+        par, k = robot.parent[i], robot.S_ind[i]
+        ap = sr.X_col(i, 5, gravity) if par < 0 else vadd(sr.X_motion(i, a[par]), cb[i])
+        qdd[i] = Dinv[i] * (uu[i] - dot(U[i], ap))
+        a[i] = list(ap)
+        a[i][k] = a[i][k] + qdd[i]
+    return qdd
+
+
+def trace_crba(robot: Robot) -> Program:
+    """M(q), n x n column-major, BOTH triangles (unlike Minv's upper-triangular contract)."""
+    p = Program()
+    n = robot.n
+    (q,) = _inputs(p, n, ("q",))
+    M = crba(SymRobot(p, robot, q))
+    for col in range(n):
+        for row in range(n):
+            p.output("M", col * n + row, M.get((min(row, col), max(row, col)), 0.0))
+    return p
+
+
+def trace_aba(robot: Robot) -> Program:
+    p = Program()
+    n = robot.n
+    q, qd, u = _inputs(p, n, ("q", "qd", "u"))
+    g = p.inp("gravity")
+    qdd = aba(SymRobot(p, robot, q), qd, u, g)
+    for i in range(n):
+        p.output("qdd", i, qdd[i])
+    return p
+
+
 TRACERS = {
     "id": lambda robot: trace_id(robot, False),
     "id_qdd": lambda robot: trace_id(robot, True),
@@ -896,6 +991,8 @@ TRACERS = {
     "fd_grad_qd": lambda robot: trace_fd_grad(robot, False, side=1),
     "fd_vjp": lambda robot: trace_fd_consumer(robot, "fd_vjp"),
     "fd_lin": lambda robot: trace_fd_consumer(robot, "fd_lin"),
+    "crba": trace_crba,
+    "aba": trace_aba,
 }
 
 # packed (float2) variants of the gradient programs

@@ -38,6 +38,9 @@ VARIANTS = {
     # consumers fused after the FD gradient (algorithms.trace_fd_consumer); in1 = lam (2n words)
     "fd_vjp":           ("AlgFdVjp",        3, 2, 0, "fd_vjp", lambda n: 5 * n),
     "fd_lin":           ("AlgFdLin",        3, 0, 0, "fd_lin", lambda n: 2 * n + 3 * n * n),
+    # further algorithms: mass matrix by CRBA (both triangles), forward dynamics by ABA (no Minv)
+    "crba":             ("AlgCrba",         1, 0, 0, "M",     lambda n: n * n),
+    "aba":              ("AlgAba",          3, 0, 0, "qdd",   lambda n: n),
 }
 
 _NAME_RE = re.compile(r"^(qdd|qd|q|u|Minv|lam)(\d+)$")
@@ -525,7 +528,8 @@ class KernelPlan:
                  pipe_warps: int = 8, pipe_sync_every: int = 256, pipe_scratch_lead: int = 160,
                  wps_tc_matmul: bool = False, only_algs=None, pipe_small_states: int = 24576,
                  pipe_small_group_flops: int = 4000, lps_min_states: int = 256, lps_force: bool = False,
-                 tps_half: bool = False, pipe_x2: bool = False):
+                 tps_half: bool = False, pipe_x2: bool = False, extras_max_flops: int = 26000,
+                 fd_via_aba: Optional[bool] = None):
         # every constructor argument except the robot: build.py hashes this into the library name, so
         # a library built with one plan is never returned for another
         self._args = {k: v for k, v in locals().items() if k not in ("self", "robot")}
@@ -638,6 +642,31 @@ class KernelPlan:
             if "fd_grad" in self.lps:
                 fams.append("lps")
             self.consumers[c] = "+".join(fams) if fams else "none"
+        # Further algorithms, thread-per-state programs: the mass matrix by the composite-rigid-body
+        # algorithm and forward dynamics by the articulated-body algorithm (O(n), no Minv).  Gate: traced flops
+        # (a program beyond ~26 k operations is a megabyte of straight-line code: the 64-link chain's CRBA is out,
+        # its ABA is in).
+        from .algorithms import TRACERS as _T
+        self.extras: Dict[str, str] = {}
+        self.extra_programs: Dict[str, Program] = {}
+        for x in ("crba", "aba"):
+            if self.only_algs is not None and x not in self.only_algs:
+                self.extras[x] = "none"
+                continue
+            prog = _T[x](robot)
+            fl = prog.op_counts()["flops"]
+            self.extras[x] = "tps" if fl <= extras_max_flops else "none"
+            if self.extras[x] == "tps":
+                self.extra_programs[x] = prog
+        # forward_dynamics served by the ABA program: the same qdd through fewer operations (iiwa14 1 691 vs 2 331
+        # traced flops, Atlas 8 758 in ONE thread vs 15 784 over the phase-split Minv + RNEA, 64-link chain 22 879 vs the
+        # rolled chain kernels).  Measured (profiles/r2_aba_crba_timings.jsonl, 65 536 states): iiwa14 10.8 vs 12.7 us,
+        # HyQ 12.8 vs 23.6 us, Atlas 59.9 vs 79.3 us, chain 422 vs 805 us; at small batches everything sits on the
+        # launch floor, so robots that have a thread-per-state FD switch only from 32 768 states on, the others from 256.
+        if fd_via_aba is None:
+            fd_via_aba = True
+        self.fd_via_aba = bool(fd_via_aba) and self.extras.get("aba") == "tps"
+        self.fd_aba_min_states = 32768 if "tps" in self.kind["fd"] else 256
         self.cps_lanes = 16 if 2 * robot.n <= 16 else 32
         # where phase-split kernels exist they are at least as fast as the latency kernels at every batch
         # size once their CTA size follows the batch (HyQ FD gradient N = 128: 8.6 vs 10.6 us, N = 512: 9.5
@@ -737,6 +766,11 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
             txt, cnt = emit_alg_struct(robot, c, sync_every=plan.tps_sync_every)
             out.append(txt)
             stats[c] = cnt
+    for x, fam in plan.extras.items():
+        if fam == "tps":
+            txt, cnt = emit_alg_struct(robot, x, p=plan.extra_programs[x], sync_every=plan.tps_sync_every)
+            out.append(txt)
+            stats[x] = cnt
     if plan.tps_half:
         for v in ("fd_grad_q", "fd_grad_qd"):
             txt, cnt = emit_alg_struct(robot, v)
@@ -841,7 +875,19 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
               pipe_call=[(None, "pipe::pipe_launch<gen::PipeMinv>(d_Minv, d_q, stride, nullptr, N, 0.f, s)")],
               lps_call=[(None, "lps::lps_launch<0, false>(d_Minv, d_q, stride, nullptr, N, 0.f, s)")])
     L.append("}")
+    xmb = lambda x: 16 if stats[x]["flops"] < 4000 else 8          # register cap of the extra programs: 128 / 255
+    L.append("cudaError_t launch_aba(float *d_qdd, const float *d_q_qd_u, int stride, int N, float g, cudaStream_t s) {")
+    L.append("    return %s;" % ("tps_launch<AlgAba, %d, %d>(d_qdd, d_q_qd_u, stride, nullptr, nullptr, N, g, s)" % (W, xmb("aba"))
+                                if plan.extras["aba"] == "tps" else "cudaErrorNotSupported"))
+    L.append("}")
+    L.append("cudaError_t launch_crba(float *d_M, const float *d_q, int stride, int N, cudaStream_t s) {")
+    L.append("    return %s;" % ("tps_launch<AlgCrba, %d, %d>(d_M, d_q, stride, nullptr, nullptr, N, 0.f, s)" % (W, xmb("crba"))
+                                if plan.extras["crba"] == "tps" else "cudaErrorNotSupported"))
+    L.append("}")
     L.append("cudaError_t launch_fd(float *d_qdd, const float *d_q_qd_u, int stride, int N, float g, cudaStream_t s) {")
+    if plan.fd_via_aba:
+        L.append("    if (options().force_kernel == kAuto && N >= %d) return launch_aba(d_qdd, d_q_qd_u, stride, N, g, s);"
+                 % plan.fd_aba_min_states)
     L += body("fd", [(None, "%s(d_qdd, d_q_qd_u, stride, nullptr, nullptr, N, g, s)" % tps("fd", "AlgFd"))],
               [(None, "wps::wps_launch<1, false>(d_qdd, d_q_qd_u, stride, nullptr, nullptr, N, g, s)")],
               pipe_call=[(None, PL("PipeFd", "d_qdd", "d_q_qd_u", "nullptr"))],
@@ -909,13 +955,17 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
         L.append("}")
 
     kinds = "\n".join('    if (!strcmp(alg, "%s")) return "%s";' % (a, k)
-                      for a, k in list(plan.kind.items()) + list(plan.consumers.items()))
+                      for a, k in list(plan.kind.items()) + list(plan.consumers.items()) + list(plan.extras.items()))
+    if plan.fd_via_aba:                               # reported by grid_kernel_kind("fd@large")
+        kinds += '\n    if (!strcmp(alg, "fd@large")) return "tps(aba)";'
     fl = "\n".join('    if (!strcmp(alg, "%s")) return %d;' % (
         a, stats[needed[a][0]]["flops"] if "tps" in plan.kind[a] else plan.pipe[needed[a][0]].flops)
         for a in plan.kind if "tps" in plan.kind[a] or "pipe" in plan.kind[a])
     fl += "\n" + "\n".join('    if (!strcmp(alg, "%s")) return %d;' % (
         c, stats[c]["flops"] if "tps" in fam else plan.pipe[c].flops)
         for c, fam in plan.consumers.items() if "tps" in fam or "pipe" in fam)
+    fl += "\n" + "\n".join('    if (!strcmp(alg, "%s")) return %d;' % (x, stats[x]["flops"])
+                            for x, fam in plan.extras.items() if fam == "tps")
     out.append("#include <cstring>\n#include <cstdlib>\n")
     out.append(_LAUNCHERS % {"launchers": "\n".join(L), "kinds": kinds, "flops": fl})
     out.append('#include "grid_abi.cuh"\n')

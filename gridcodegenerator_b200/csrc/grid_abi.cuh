@@ -139,6 +139,29 @@ int grid_forward_dynamics_device(float *d_qdd, const float *d_q_qd_u, int stride
     return 0;
 }
 
+/* further algorithms: thread-per-state programs where the robot has them */
+int grid_crba_device(float *d_M, const float *d_q, int stride, int num_timesteps, void *stream) {
+    if (int rc = GRID_NS::check_args(d_M, d_q, stride, GRID_N, num_timesteps)) return rc;
+    if (num_timesteps == 0) return 0;
+    cudaError_t e = GRID_NS::gen::launch_crba(d_M, d_q, stride, num_timesteps, (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported)
+        return GRID_NS::fail_msg("no mass-matrix (CRBA) program for this robot: grid_kernel_kind(\"crba\") is \"none\"");
+    if (e != cudaSuccess) return GRID_NS::fail("crba_kernel", e);
+    GRID_NS::g_launches.fetch_add(1);
+    return 0;
+}
+
+int grid_aba_device(float *d_qdd, const float *d_q_qd_u, int stride, int num_timesteps, float gravity, void *stream) {
+    if (int rc = GRID_NS::check_args(d_qdd, d_q_qd_u, stride, 3 * GRID_N, num_timesteps)) return rc;
+    if (num_timesteps == 0) return 0;
+    cudaError_t e = GRID_NS::gen::launch_aba(d_qdd, d_q_qd_u, stride, num_timesteps, gravity, (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported)
+        return GRID_NS::fail_msg("no articulated-body (ABA) program for this robot: grid_kernel_kind(\"aba\") is \"none\"");
+    if (e != cudaSuccess) return GRID_NS::fail("aba_kernel", e);
+    GRID_NS::g_launches.fetch_add(1);
+    return 0;
+}
+
 int grid_inverse_dynamics_gradient_device(float *d_dc_du, const float *d_q_qd, int stride, const float *d_qdd,
                                           int num_timesteps, float gravity, void *stream) {
     if (int rc = GRID_NS::check_args(d_dc_du, d_q_qd, stride, 2 * GRID_N, num_timesteps)) return rc;
@@ -448,6 +471,8 @@ static int launch_by_name(const char *alg, float *d_out, const float *d_in, int 
     if (!strcmp(alg, "id")) return grid_inverse_dynamics_device(d_out, d_in, stride, d_in1, N, gravity, s);
     if (!strcmp(alg, "minv")) return grid_direct_minv_device(d_out, d_in, stride, N, s);
     if (!strcmp(alg, "fd")) return grid_forward_dynamics_device(d_out, d_in, stride, N, gravity, s);
+    if (!strcmp(alg, "aba")) return grid_aba_device(d_out, d_in, stride, N, gravity, s);
+    if (!strcmp(alg, "crba")) return grid_crba_device(d_out, d_in, stride, N, s);
     if (!strcmp(alg, "id_grad")) return grid_inverse_dynamics_gradient_device(d_out, d_in, stride, d_in1, N, gravity, s);
     if (!strcmp(alg, "fd_grad")) return grid_forward_dynamics_gradient_device(d_out, d_in, stride, d_in1, d_in2, N, gravity, s);
     if (!strcmp(alg, "fd_vjp")) return grid_forward_dynamics_gradient_vjp_device(d_out, d_in, stride, d_in1, N, dt, gravity, s);

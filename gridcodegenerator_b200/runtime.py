@@ -49,6 +49,9 @@ EXPORTS = {
     "grid_forward_dynamics_linearize_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                                               ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                                               ctypes.c_void_p]),
+    "grid_crba_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "grid_aba_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                       ctypes.c_void_p]),
     "grid_forward_dynamics_gradient_vjp": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float]),
     "grid_forward_dynamics_linearize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float]),
     "grid_graph_create": (ctypes.c_void_p, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
@@ -393,6 +396,21 @@ class GridEngine:
         T, stride = self._shape("forward_dynamics_device", q_qd_u, 3 * n, num_timesteps, stride, [("qdd", qdd, n)])
         self._check(self.lib.grid_forward_dynamics_device(_ptr(qdd), _ptr(q_qd_u), stride, T, gravity,
                                                           _stream(stream)), "forward_dynamics_device")
+        return qdd
+
+    # ---- further algorithms (include/grid_b200.h): mass matrix by CRBA, forward dynamics by ABA -------------
+    def crba_device(self, M, q, num_timesteps=None, stride=None, stream=None):
+        """M[n*n] per state: the joint-space mass matrix, column-major, both triangles."""
+        n = self.n
+        T, stride = self._shape("crba_device", q, n, num_timesteps, stride, [("M", M, n * n)])
+        self._check(self.lib.grid_crba_device(_ptr(M), _ptr(q), stride, T, _stream(stream)), "crba_device")
+        return M
+
+    def aba_device(self, qdd, q_qd_u, num_timesteps=None, stride=None, gravity=9.81, stream=None):
+        """qdd[n] per state by the articulated-body algorithm (same contract as forward_dynamics_device)."""
+        n = self.n
+        T, stride = self._shape("aba_device", q_qd_u, 3 * n, num_timesteps, stride, [("qdd", qdd, n)])
+        self._check(self.lib.grid_aba_device(_ptr(qdd), _ptr(q_qd_u), stride, T, gravity, _stream(stream)), "aba_device")
         return qdd
 
     def inverse_dynamics_gradient_device(self, dc_du, q_qd, qdd=None, num_timesteps=None, stride=None, gravity=9.81,

@@ -99,6 +99,18 @@ int grid_forward_dynamics_gradient_vjp_device(float *d_out, const float *d_q_qd_
 int grid_forward_dynamics_linearize_device(float *d_out, const float *d_q_qd_u, int stride, int num_timesteps, float dt,
                                            float gravity, void *stream);
 
+/* ---- further algorithms (what the GRiD family added after this reference) ----
+ * No counterpart in /root/reference; pinned to it through its own algorithms (tests/golden/*_mass.npz: the columns
+ * of M from the reference's RNEA; M Minv = I; ABA = Minv (u - c)).
+ * grid_crba_device: joint-space mass matrix M(q) by the composite-rigid-body algorithm.
+ *   d_q: q per state (stride words apart); d_M: n*n per state, column-major, BOTH triangles.
+ * grid_aba_device: qdd = FD(q, qd, u) by the articulated-body algorithm (O(n), no Minv); same inputs, output and
+ *   conventions (gravity, joint damping) as grid_forward_dynamics_device.  Where it is the faster program
+ *   grid_forward_dynamics_device itself runs it for large batches (grid_kernel_kind("fd@large") == "tps(aba)").
+ * Available when grid_kernel_kind("crba") / ("aba") != "none"; otherwise they fail with a message. */
+int grid_crba_device(float *d_M, const float *d_q, int stride, int num_timesteps, void *stream);
+int grid_aba_device(float *d_qdd, const float *d_q_qd_u, int stride, int num_timesteps, float gravity, void *stream);
+
 /* ---- gridData-style handle (reference init_gridData / init_grid / close_grid) ------- */
 typedef struct grid_data grid_data;
 

@@ -54,6 +54,13 @@ VARIANTS = {
     "x2m_g4000": dict(pipe_x2=dict(max_live=110, remat_gap=200, lead=80), pipe_opts=dict(group_flops=4000)),
     "x2m_ml125": dict(pipe_x2=dict(max_live=125, remat_gap=100, lead=40)),
     "x2m_gap100": dict(pipe_x2=dict(max_live=110, remat_gap=100, lead=40)),
+    # iiwa14 (VARIANT_ROBOT=iiwa14 VARIANT_FORCE=pipe): few LARGE column groups - every program under the 64 KB that
+    # stay in the instruction cache, scratch words read by 1-3 programs instead of 7
+    "i_g2800":   dict(pipe_algs=("fd_grad",), pipe_opts=dict(single_stage_max_flops=0, group_flops=2800)),
+    "i_g4200":   dict(pipe_algs=("fd_grad",), pipe_opts=dict(single_stage_max_flops=0, group_flops=4200)),
+    "i_g9000":   dict(pipe_algs=("fd_grad",), pipe_opts=dict(single_stage_max_flops=0, group_flops=9000)),
+    "i_g4200_w16": dict(pipe_algs=("fd_grad",), pipe_opts=dict(single_stage_max_flops=0, group_flops=4200), pipe_warps=16),
+    "i_g2800_w16": dict(pipe_algs=("fd_grad",), pipe_opts=dict(single_stage_max_flops=0, group_flops=2800), pipe_warps=16),
     "x2m_w4":    dict(pipe_x2=dict(max_live=110, remat_gap=200, lead=80), pipe_warps=4, pipe_min_blocks=(2, 2)),
 }
 
@@ -93,6 +100,8 @@ def run(names):
     for name in names:
         try:
             eng = GridEngine(robot, plan=plan_for(robot, name), tag="_x" + name)
+            if os.environ.get("VARIANT_FORCE"):
+                eng.set_option("GRID_FORCE_KERNEL", os.environ["VARIANT_FORCE"])
             eng.forward_dynamics_gradient_device(out, x)
             torch.cuda.synchronize()
             err = float(np.abs(out[:512].cpu().numpy() - ref).max() / np.abs(ref).max())
@@ -105,6 +114,7 @@ def run(names):
                 res["evals_per_s_N16384"] = 16384 / res["us_N16384"] * 1e6
                 print(json.dumps(res), flush=True)
                 continue
+            res["kind"] = eng.kernel_kind(ALG)
             for N in (65536, 8192, 128):
                 us = eng.time_launches(ALG, out, x, num_timesteps=N, stride=3 * n, reps=20 if N > 1000 else 100)
                 res["us_N%d" % N] = float(np.median(us))
@@ -116,7 +126,7 @@ def run(names):
                 res["tasks"] = st.get("tasks")
                 res["x2_live"] = st.get("x2_live")
                 per = {}
-                for stage, cnt in ((0, 8), (1, 40)):
+                for stage, cnt in ((0, sum(1 for t in st.get("tasks", []) if t[1] == 0)), (1, sum(1 for t in st.get("tasks", []) if t[1] == 1))):
                     for k in range(cnt):
                         eng.set_option("GRID_PIPE_ONLY_TASK", str(100 * stage + k))
                         us = float(np.median(eng.time_launches(ALG, out, x, num_timesteps=65536, stride=3 * n, reps=5)))
