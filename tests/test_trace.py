@@ -45,6 +45,10 @@ def _run(robot, key, q, qd, u, qdd, dtype):
         ref = O.batch(robot, "fd_grad", q, qd, u)
         return (p.evaluate(_ins(q=q, qd=qd, u=u), dtype)["df_du"],
                 ref[:, :nn] if key == "fd_grad_q" else ref[:, nn:], "fd_grad")
+    if key == "crba":                            # further algorithms
+        return p.evaluate(_ins(q=q), dtype)["M"], O.batch(robot, "crba", q), "minv"
+    if key == "aba":
+        return p.evaluate(_ins(q=q, qd=qd, u=u), dtype)["qdd"], O.batch(robot, "fd", q, qd, u), "fd"
     if key in ("fd_vjp", "fd_lin"):              # consumers fused after the FD gradient
         lam = np.random.default_rng(2).uniform(-3, 3, (N, 2 * robot.n))
         ins = _ins(q=q, qd=qd, u=u, lam=lam)
