@@ -587,7 +587,11 @@ class KernelPlan:
         variants = {"id": ("id", "id_qdd"), "minv": ("minv",), "fd": ("fd",), "id_grad": ("id_grad", "id_grad_qdd"),
                     "fd_grad": ("fd_grad", "fd_grad_qdd_minv")}
         for a in want:
-            pvs = [PipeVariant(robot, v, **self.pipe_opts) for v in variants[a]]
+            pvs = []
+            for v in variants[a]:                 # stop at the first variant that does not fit (long chains: each
+                pvs.append(PipeVariant(robot, v, **self.pipe_opts))      # rejected candidate costs a full trace)
+                if not pvs[-1].feasible:
+                    break
             if all(pv.feasible for pv in pvs):
                 for pv in pvs:
                     self.pipe[pv.variant] = pv

@@ -393,13 +393,21 @@ class PipeVariant:
         self.feasible = True
         sc_base = 0
         for ci, ids in enumerate(components(robot)):
-            pf, runs = _trace_full(robot, ids, alg, use_qdd)
-            full = PipeTask("c%d_full" % ci, 0, pf, runs, ci)
-            if alg not in GRAD_LIKE or full.flops <= single_stage_max_flops:
-                if full.flops > stage_a_max_flops:
-                    self.feasible = False
-                self.tasks.append(full)
-                continue
+            # a gradient whose dense operation count is more than 12x the single-stage limit is two-stage for sure
+            # (tracing folds 4-5x away): skip the full trace, which for a 64-link chain costs tens of seconds
+            hopeless = False
+            if alg in GRAD_LIKE:
+                from .algorithms import algorithmic_flops
+                dense = algorithmic_flops(subrobot(robot, ids))["id_grad" if alg in ("id_grad",) else "fd_grad"]
+                hopeless = dense > 12 * max(single_stage_max_flops, 1)
+            if not hopeless:
+                pf, runs = _trace_full(robot, ids, alg, use_qdd)
+                full = PipeTask("c%d_full" % ci, 0, pf, runs, ci)
+                if alg not in GRAD_LIKE or full.flops <= single_stage_max_flops:
+                    if full.flops > stage_a_max_flops:
+                        self.feasible = False
+                    self.tasks.append(full)
+                    continue
             # two stages: A = state program, B = groups of du-columns
             pa, ex, sub, runs_a = _trace_stage_a(robot, ids, alg, use_qdd)
             nc = sub.n
@@ -408,6 +416,11 @@ class PipeVariant:
             for j in range(nc):
                 pb, _ = _trace_stage_b(robot, ids, sub, [j], alg, ex)
                 cost.append(pb.op_counts()["flops"])
+                if cost[-1] > stage_a_max_flops:     # a single column too long for one thread (64-link chain): the
+                    self.feasible = False            # variant is unusable, no point in tracing the other columns
+                    break
+            if not self.feasible:
+                break
             groups, cur, acc = [], [], 0
             for j in range(nc):
                 if cur and acc + cost[j] > group_flops:

@@ -45,3 +45,16 @@ def golden_df_du(z):
 def golden_big_count(z):
     """States for which the n x n / n x 2n matrices other than df_du are stored."""
     return int(z["n_big"]) if "n_big" in z.files else z["q"].shape[0]
+
+
+_PLANS = {}
+
+
+def cached_plan(name, **kw):
+    """KernelPlan of a named robot, built once per test process: the plan of the 64-link chain traces every
+    phase-split candidate before rejecting it (two minutes), and several test modules look at the same default plans."""
+    from gridcodegenerator_b200.codegen import KernelPlan
+    key = (name, repr(sorted(kw.items())))
+    if key not in _PLANS:
+        _PLANS[key] = KernelPlan(load_named_robot(name), **kw)
+    return _PLANS[key]

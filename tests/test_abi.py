@@ -111,11 +111,12 @@ def test_kernel_plan_families_per_robot():
     (or when forced, for the test builds), fused consumers wherever the FD gradient has tps / pipe / lps kernels, a
     second set of column programs for small Atlas batches, and `only_algs` for experiment builds."""
     from gridcodegenerator_b200.codegen import KernelPlan
-    chain = KernelPlan(load_named_robot("chain64"))
+    from helpers import cached_plan
+    chain = cached_plan("chain64")
     assert chain.lps == {"minv", "fd", "id_grad", "fd_grad"} and chain.kind["id"] == "tps"
     assert all(k.endswith("+lps") for a, k in chain.kind.items() if a != "id")
     assert chain.consumers == {"fd_vjp": "lps", "fd_lin": "lps"}
-    iiwa = KernelPlan(load_named_robot("iiwa14"))
+    iiwa = cached_plan("iiwa14")
     assert not iiwa.lps and iiwa.consumers == {"fd_vjp": "tps", "fd_lin": "tps"} and iiwa.pipe_small is None
     forced = KernelPlan(load_named_robot("pchain4"), lps_force=True)
     assert forced.lps and forced.lps_forced_only and "lps" in forced.consumers["fd_vjp"]

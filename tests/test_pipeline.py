@@ -74,13 +74,14 @@ def test_plan_policy():
     """Single-tree robots with thread-per-state programs keep them; forests (Atlas: torso+arms, two
     legs; HyQ: four legs) get one thread per (state, tree) for every algorithm and column groups
     where a tree's gradient does not fit one thread; a 64-link chain's columns are too long."""
-    assert KernelPlan(load_named_robot("iiwa14")).pipe == {}
+    from helpers import cached_plan
+    assert cached_plan("iiwa14").pipe == {}
     for name in ("atlas", "hyq"):
-        plan = KernelPlan(load_named_robot(name))
+        plan = cached_plan(name)
         assert all("pipe" in plan.kind[a] for a in ("minv", "fd", "id_grad", "fd_grad")), plan.kind
         assert plan.kind["id"] == "tps"          # measured: the single-thread RNEA is faster (23 vs 31 us, Atlas 65 536)
     assert not PipeVariant(load_named_robot("chain64"), "id_grad").feasible
-    assert KernelPlan(load_named_robot("chain64")).pipe == {}
+    assert cached_plan("chain64").pipe == {}
 
 
 @pytest.mark.parametrize("variant", ["fd_grad", "id_grad", "fd_vjp", "fd_lin"])
