@@ -671,6 +671,10 @@ class KernelPlan:
             fd_via_aba = True
         self.fd_via_aba = bool(fd_via_aba) and self.extras.get("aba") == "tps"
         self.fd_aba_min_states = 32768 if "tps" in self.kind["fd"] else 256
+        # largest batch the phase-split kernels take when a thread-per-state program exists as well (see
+        # generate_translation_unit.body): Minv / FD up to 32 768 states, gradients while the output fits ~96 MB of L2
+        self.pipe_max_states = {"minv": 32768, "fd": 32768, "id_grad": (96 << 20) // (8 * robot.n * robot.n),
+                                "fd_grad": (96 << 20) // (8 * robot.n * robot.n)}
         self.cps_lanes = 16 if 2 * robot.n <= 16 else 32
         # where phase-split kernels exist they are at least as fast as the latency kernels at every batch
         # size once their CTA size follows the batch (HyQ FD gradient N = 128: 8.6 vs 10.6 us, N = 512: 9.5
@@ -824,7 +828,12 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
             lines.append("    }")
         if "pipe" in plan.kind[a]:
             others = plan.kind[a] != "pipe"
-            lines.append("    if (%s) {" % ("use_pipe(N)" if others else "true"))
+            # where a thread-per-state program exists too, the phase-split kernels keep the batches they win
+            # (profiles/r2_hyq_kernel_families.jsonl: HyQ Minv 8.4 vs 10.5 us at 128 states but 24 vs 17 us at 65 536;
+            # gradients 44 vs 54 us at 65 536 but 305 vs 177 us at 262 144, where the output no longer fits the L2 and
+            # the 48-byte column fragments of four leg programs reach DRAM as partial sectors)
+            cap = plan.pipe_max_states.get(a, 0) if has_tps(a) else 0
+            lines.append("    if (%s) {" % (("use_pipe(N, %d)" % cap) if others else "true"))
             lines += ["        %sreturn %s;" % ("if (%s) " % c if c else "", e) for c, e in pipe_call]
             lines.append("    }")
         if has_tps(a) and has_wps(a):
@@ -855,10 +864,10 @@ def generate_translation_unit(robot: Robot, plan: Optional[KernelPlan] = None,
              "    if (f != kAuto) return f == kCps;\n"
              "    return N <= %d;\n}" % plan.cps_max_states)
     L.append("// large batches of robots with phase-split kernels (grid_pipe.cuh)\n"
-             "static bool use_pipe(int N) {\n"
+             "static bool use_pipe(int N, int max_states = 0) {\n"
              "    const int f = options().force_kernel;\n"
              "    if (f != kAuto) return f == kPipe;\n"
-             "    return N >= %d;\n}" % plan.pipe_min_states)
+             "    return N >= %d && (max_states <= 0 || N <= max_states);\n}" % plan.pipe_min_states)
     L.append("// serial chains without thread-per-state programs: lane-per-state kernels with rolled joint loops\n"
              "static bool use_lps(int N) {\n"
              "    const int f = options().force_kernel;\n"

@@ -329,6 +329,14 @@ class GridEngine:
         alg may end in "@graph": the launch is captured once and the timed launches replay the graph."""
         stride = int(inp.shape[-1]) if stride is None else stride
         T = int(inp.shape[0]) if num_timesteps is None else num_timesteps
+        n = self.n
+        words = {"id": n, "minv": n * n, "fd": n, "aba": n, "crba": n * n, "id_grad": 2 * n * n, "fd_grad": 2 * n * n,
+                 "fd_vjp": 5 * n, "fd_lin": 2 * n + 3 * n * n, "noop": 0}.get(alg.split("@")[0])
+        if words is None:
+            raise GridError("time_launches: unknown algorithm %r" % alg)
+        if hasattr(out, "numel") and out.numel() < T * words:
+            raise GridError("time_launches: the output buffer holds %d floats, %d states of %s need %d"
+                            % (out.numel(), T, alg, T * words))
         buf = (ctypes.c_float * reps)()
         self._sync_options()
         self._check(self.lib.grid_time_launches(alg.encode(), _ptr(out), _ptr(inp), stride, T, gravity, reps, buf),
