@@ -61,6 +61,11 @@ VARIANTS = {
     "i_g9000":   dict(pipe_algs=("fd_grad",), pipe_opts=dict(single_stage_max_flops=0, group_flops=9000)),
     "i_g4200_w16": dict(pipe_algs=("fd_grad",), pipe_opts=dict(single_stage_max_flops=0, group_flops=4200), pipe_warps=16),
     "i_g2800_w16": dict(pipe_algs=("fd_grad",), pipe_opts=dict(single_stage_max_flops=0, group_flops=2800), pipe_warps=16),
+    # iiwa14 thread-per-state FD gradient at 9 / 10 / 12 resident warps per SM (224 / 200 / 168 registers)
+    "i_mb8":     dict(tps_min_blocks={"fd_grad": 8}),
+    "i_mb9":     dict(tps_min_blocks={"fd_grad": 9}),
+    "i_mb10":    dict(tps_min_blocks={"fd_grad": 10}),
+    "i_mb12":    dict(tps_min_blocks={"fd_grad": 12}),
     "x2m_w4":    dict(pipe_x2=dict(max_live=110, remat_gap=200, lead=80), pipe_warps=4, pipe_min_blocks=(2, 2)),
 }
 
