@@ -369,6 +369,22 @@ def test_packed_two_states_per_lane_column_programs(N, monkeypatch):
     assert np.array_equal(g[1:N + 1], out)
 
 
+@pytest.mark.parametrize("chunk", [2048, 8192])
+def test_pipe_chunk_major_item_order_is_bit_identical(chunk, monkeypatch):
+    """GRID_PIPE_ORDER_CHUNK (experiment, off by default): the stage-1 items of a two-stage launch walked chunk by
+    chunk in descending order, ragged last chunk first - another order of the same independent items."""
+    robot = load_named_robot("atlas")
+    eng = get_engine(robot)
+    N = 20000 + 37
+    q, qd, u, _ = make_states(robot.n, N, 41)
+    base = run_alg(eng, "fd_grad", q, qd, u)
+    monkeypatch.setenv("GRID_PIPE_ORDER_CHUNK", str(chunk))
+    assert np.array_equal(run_alg(eng, "fd_grad", q, qd, u), base)
+    assert np.array_equal(run_alg(eng, "id_grad", q, qd, u), run_alg(eng, "id_grad", q, qd, u))
+    monkeypatch.delenv("GRID_PIPE_ORDER_CHUNK")
+    assert np.array_equal(run_alg(eng, "fd_grad", q, qd, u), base)
+
+
 @pytest.mark.parametrize("name,N", [("atlas", 1000), ("hyq", 4099)])
 def test_pipe_fused_variant_matches_staged(name, N, monkeypatch):
     """The SM-partitioned single-kernel variant (GRID_PIPE_MODE=fused: stage-1 warps wait on
