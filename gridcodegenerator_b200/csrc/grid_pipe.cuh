@@ -135,7 +135,7 @@ template <class P, int STAGE>
 __global__ void __launch_bounds__(32 * P::WARPS, STAGE == 0 ? P::MINB0 : P::MINB1)
 pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stride0, const float *__restrict__ d_in1,
             float *__restrict__ scratch, unsigned int *__restrict__ ticket, int num_states, int ntiles, int nblk,
-            float gravity, float dt, const float *__restrict__ d_in2, int stagger_ns, int task0, int ntasks, int order_blk) {
+            float gravity, float dt, const float *__restrict__ d_in2, int stagger_ns, int task0, int ntasks, int order_blk, int no_store) {
     using S = PipeShape<P>;
     // states per tile: a stage-1 warp of a P::X2 variant runs 64 states (two per lane, packed FP32 instructions);
     // `ntiles` counts tiles of that size.  Scratch rows then hold 64 states: [tile of 64][word][64].
@@ -205,8 +205,8 @@ pipe_kernel(float *__restrict__ d_out, const float *__restrict__ d_in0, int stri
         // lines of the program), so a warp past the last tile cannot sit out: it recomputes the
         // last tile and stores nothing (its scratch writes duplicate the owner's values).
         const int my_tile = blk * (int)(blockDim.x >> 5) + warp;
-        const bool owner = my_tile < ntiles;
-        const int tile = owner ? my_tile : ntiles - 1;
+        const bool owner = my_tile < ntiles && !no_store;      // no_store (profiling): every output store predicated off
+        const int tile = my_tile < ntiles ? my_tile : ntiles - 1;
         const long long first = (long long)tile * SPT;
         const int cnt = min(SPT, num_states - (int)first);
         if (STAGE == 0) {
@@ -265,7 +265,9 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
     if (ntasks_all == 0) return cudaSuccess;
     // profiling (GRID_PIPE_ONLY_TASK = 100 * stage + task): only that task program runs, the other stage is skipped
     int task0 = 0, ntasks = ntasks_all;
-    if (const int only = options().pipe_only_task; only >= 0) {
+    // GRID_PIPE_ONLY_TASK = 1000: all tasks, but no output stores (what the writes cost; results are not produced)
+    const int no_store = options().pipe_only_task == 1000;
+    if (const int only = options().pipe_only_task; only >= 0 && only < 1000) {
         if (only / 100 != STAGE || only % 100 >= ntasks_all) return cudaSuccess;
         task0 = only % 100;
         ntasks = 1;
@@ -327,7 +329,7 @@ cudaError_t pipe_stage_launch(float *d_out, const float *d_in0, int stride0, con
     }
     kern<<<blocks, 32 * w, warp_smem * w, stream>>>(d_out, d_in0, stride0, d_in1, scratch,
                                                     items > cap ? ticket : nullptr, num_states, ntiles, nblk, gravity,
-                                                    dt, d_in2, options().pipe_stagger_ns, task0, ntasks, order_blk);
+                                                    dt, d_in2, options().pipe_stagger_ns, task0, ntasks, order_blk, no_store);
     g_kernel_launches.fetch_add(1);
     return cudaGetLastError();
 }
