@@ -45,13 +45,21 @@ __device__ __forceinline__ void st_release(int *p, int v) {
 // the pair is short, one of K = 32 / Wp states per step: all index arithmetic is hoisted out of the
 // loop, whose body is one shared load, one global store and one predicate with immediate offsets
 // (the element-wise mapping it replaces cost 9 instructions per word: 19 % of the iiwa14 kernel).
+// Cache policy of the output stores: ".cs" (streaming, evict-first).  The outputs are written once and never read by
+// the kernels, while the scratch words and the INSTRUCTION STREAM live in the same L2: with default write-back stores
+// the 472 MB of an Atlas FD gradient push them out.  Measured (profiles/r2_atlas_output_store_policy.jsonl, Atlas FD
+// gradient): 735 vs 749 us at 65 536 states, 212.5 vs 222.8 at 16 384, 110.7 vs 128.0 at 8 192 (the per-GPU shard of
+// a strongly scaled job: -14 %); ".wt" changes nothing.  -DGRID_PIPE_ST_POLICY=\"\" restores write-back.
+#ifndef GRID_PIPE_ST_POLICY
+#define GRID_PIPE_ST_POLICY ".cs"
+#endif
 // predicated global store without a branch: `if (k < left) *p = v`
 __device__ __forceinline__ void st_if_lt(float *p, float v, int k, int left) {
-    asm volatile("{ .reg .pred q; setp.lt.s32 q, %2, %3; @q st.global.f32 [%0], %1; }" ::"l"(p), "f"(v), "r"(k), "r"(left)
+    asm volatile("{ .reg .pred q; setp.lt.s32 q, %2, %3; @q st.global" GRID_PIPE_ST_POLICY ".f32 [%0], %1; }" ::"l"(p), "f"(v), "r"(k), "r"(left)
                  : "memory");
 }
 __device__ __forceinline__ void st_if_lt(float2 *p, float2 v, int k, int left) {
-    asm volatile("{ .reg .pred q; setp.lt.s32 q, %3, %4; @q st.global.v2.f32 [%0], {%1, %2}; }" ::"l"(p), "f"(v.x),
+    asm volatile("{ .reg .pred q; setp.lt.s32 q, %3, %4; @q st.global" GRID_PIPE_ST_POLICY ".v2.f32 [%0], {%1, %2}; }" ::"l"(p), "f"(v.x),
                  "f"(v.y), "r"(k), "r"(left)
                  : "memory");
 }
