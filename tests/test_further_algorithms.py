@@ -67,6 +67,25 @@ def test_plan_lists_the_further_algorithms():
     assert plan.extras == {"crba": "none", "aba": "none"}
 
 
+def test_launchers_route_by_batch_size():
+    """Generated launchers (HyQ has thread-per-state AND phase-split kernels): Minv / FD leave the phase-split kernels
+    above 32 768 states, the gradients when the output outgrows the L2, forward dynamics takes the ABA program for
+    large batches unless a kernel family is forced."""
+    import re
+    from gridcodegenerator_b200.codegen import generate_translation_unit
+    from helpers import cached_plan
+    robot = load_named_robot("hyq")
+    plan = cached_plan("hyq")
+    assert plan.pipe_max_states["minv"] == 32768 and plan.pipe_max_states["fd_grad"] == (96 << 20) // (8 * 144)
+    src, _ = generate_translation_unit(robot, plan)
+    body = {m.group(1): m.group(0) for m in re.finditer(r"cudaError_t launch_(\w+)\(.*?\n}\n", src, re.S)}
+    assert "use_pipe(N, 32768)" in body["minv"] and "use_pipe(N, 32768)" in body["fd"]
+    assert "use_pipe(N, %d)" % plan.pipe_max_states["fd_grad"] in body["fd_grad"]
+    assert "force_kernel == kAuto && N >= 32768) return launch_aba" in body["fd"]
+    assert "tps_launch<AlgAba" in body["aba"] and "tps_launch<AlgCrba" in body["crba"]
+    assert 'if (!strcmp(alg, "fd@large")) return "tps(aba)";' in src
+
+
 # ---- GPU half -------------------------------------------------------------------------------------------
 def _engine(name):
     import torch
